@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- FEM loss+grad throughput of the fused sm_100a kernels (and the reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path (fused Poisson energy loss + gradient w.r.t. u) over one
+batch of synthetic input.  Default workload = BASELINE.json configs[1]: Poisson 2-D parametric,
+256 x 256 Q1 mesh, batch 64 per GPU, KL log-diffusivity, inputs (u, nu, f, bc1, bc2) fp32.
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md section 8.
+  value     GDOF/s, whole job, inputs resident in HBM, K launches timed by CUDA events
+            (replayed from one CUDA graph so the 15-us kernels are not host-launch bound)
+  e2e       same metric through the public module API with PINNED HOST buffers: H2D of the
+            step's five fields + launch + D2H of the loss inside the timed region
+  roofline  algorithmic bytes (24 B/DOF) / measured launch duration vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle (= reference conv path restated, torch CPU) on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nsd, size, batch per GPU, bytes/DOF fwd+bwd, description)
+    "poisson2d_param_256_b64": (2, 256, 64, 24, "Poisson 2D parametric 256x256 Q1, KL log-diffusivity, batch 64/GPU"),
+    "poisson2d_512_b16": (2, 512, 16, 24, "Poisson 2D 512x512 Q1, batch 16/GPU (roofline point)"),
+    "poisson2d_64_b1": (2, 64, 1, 24, "Poisson 2D non-parametric 64x64 (configs[0])"),
+    "poisson3d_param_64_b16": (3, 64, 16, 20, "Poisson 3D parametric 64^3 Q1 hex, batch 16/GPU (u, source, sink, f)"),
+    "poisson3d_128_b1": (3, 128, 1, 24, "Poisson 3D 128^3, variable nu, f, two masks (roofline point)"),
+    "poisson3d_256_b1": (3, 256, 1, 20, "Poisson 3D non-parametric 256^3 (u, nu, bc1, f)"),
+}
+DEFAULT = "poisson2d_param_256_b64"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:   # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:   # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:   # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(name, device, seed):
+    import torch
+    from diffnet_b200.synthetic import poisson2d_parametric_batch, poisson3d_parametric_batch
+    nsd, size, B, _, _ = WORKLOADS[name]
+    if nsd == 2:
+        u, inputs, f = poisson2d_parametric_batch(B, size, device, seed)
+        return dict(u=u, nu=inputs[:, 0:1], f=f, dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)],
+                    _fields=[u, inputs, f])
+    u, src, sink, f = poisson3d_parametric_batch(B, size, device, seed)
+    if name == "poisson3d_param_64_b16":       # IBN_3D.py:114-136: nu == 1
+        return dict(u=u, f=f, dirichlet=[(sink, 0.0), (src, 1.0)], _fields=[u, src, sink, f])
+    g = torch.Generator(device="cpu").manual_seed(seed + 7)
+    nu = torch.exp(0.5 * torch.randn(u.shape, generator=g)).to(device)
+    if name == "poisson3d_256_b1":             # solve_in_object_3d.py:75-102
+        return dict(u=u, nu=nu, f=f + 500.0, dirichlet=[(src, 0.0)], c_k=0.5, _fields=[u, nu, src, f])
+    return dict(u=u, nu=nu, f=f, dirichlet=[(sink, 0.0), (src, 1.0)], _fields=[u, nu, src, sink, f])
+
+
+def make_fem(name):
+    from diffnet_b200 import DiffNet2DFEM, DiffNet3DFEM
+    nsd, size, B, _, _ = WORKLOADS[name]
+    return (DiffNet2DFEM if nsd == 2 else DiffNet3DFEM)(None, domain_size=size, batch_size=B)
+
+
+def call_kwargs(d):
+    return {k: v for k, v in d.items() if not k.startswith("_") and k != "u"}
+
+
+# ------------------------------------------------------------------------------------ oracle legs
+def oracle_step_time(name, sample_B, threads, repeats=3):
+    """fwd+bwd of the oracle (reference conv path restated) on the CPU; best of `repeats`."""
+    import torch
+    from oracle import losses as OL
+    from oracle.fem import Q1Oracle
+    nsd, size, B, _, _ = WORKLOADS[name]
+    torch.set_num_threads(threads)
+    d = make_inputs_cpu(name, sample_B)
+    o = Q1Oracle(nsd=nsd, domain_size=size)
+    kw = call_kwargs(d)
+    best = float("inf")
+    for i in range(repeats + 1):
+        u = d["u"].clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        loss = OL.energy_loss(o, u, **kw)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = min(best, dt)
+    dof = sample_B * size ** nsd
+    return best, dof
+
+
+def make_inputs_cpu(name, sample_B):
+    import torch
+    nsd, size, B, _, _ = WORKLOADS[name]
+    saved = WORKLOADS[name]
+    WORKLOADS[name] = (nsd, size, sample_B) + saved[3:]
+    try:
+        return make_inputs(name, torch.device("cpu"), seed=99)
+    finally:
+        WORKLOADS[name] = saved
+
+
+def cpu_sample_batch(name):
+    nsd, size, B, _, _ = WORKLOADS[name]
+    dof_budget = 1.5e6 if nsd == 2 else 3e5      # ~1-3 s per oracle step on a few dozen cores
+    return max(1, min(B, int(dof_budget // (size ** nsd)) or 1))
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port of DiffNetFEM.py + loss body; the
+    reference is Python and /root/reference does not exist on the GPU box)."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    nsd, size, B, bpd, desc = WORKLOADS[name]
+    threads = os.cpu_count() or 1
+    sB = cpu_sample_batch(name)
+    torch.set_num_threads(threads)
+    from oracle import losses as OL
+    from oracle.fem import Q1Oracle
+    d = make_inputs_cpu(name, sB)
+    o = Q1Oracle(nsd=nsd, domain_size=size)
+    kw = call_kwargs(d)
+
+    def step():
+        u = d["u"].clone().requires_grad_(True)
+        OL.energy_loss(o, u, **kw).backward()
+    # bounded sample: shrink it until (K + W) steps fit in ~2 minutes of CPU time
+    step()
+    t0 = time.perf_counter(); step(); t1 = time.perf_counter() - t0
+    budget, K, W = 120.0, args.steps, args.warmup
+    if t1 * (K + W) > budget and sB > 1:
+        sB = max(1, int(sB * budget / (t1 * (K + W))))
+        d = make_inputs_cpu(name, sB)
+        kw = call_kwargs(d)
+        step()
+        t0 = time.perf_counter(); step(); t1 = time.perf_counter() - t0
+    if t1 * (K + W) > budget:
+        K = max(1, int(budget / t1) - W)
+    args.steps = K
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    dof = sB * size ** nsd
+    val = dof * args.steps / dt / 1e9
+    sample = f"B={sB} of {B} samples per step ({dof} DOF), fwd+bwd w.r.t. u, torch {torch.__version__} CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": "FEM loss+grad throughput", "value": val, "unit": "GDOF/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "desc": desc, "cpu_sample": sample},
+        "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    name = args.workload
+    nsd, size, B, bpd, desc = WORKLOADS[name]
+    fem = make_fem(name)
+    dof_step = B * size ** nsd                     # per GPU per step
+    step_bytes = dof_step * bpd
+    # rotate input sets so that every step streams from HBM, not from the 126 MB L2
+    nsets = max(2, int(-(-400e6 // step_bytes)))
+    nsets = min(nsets, 64)
+    sets = [make_inputs(name, dev, seed=1234 + 17 * rank + i) for i in range(nsets)]
+    kws = [call_kwargs(s) for s in sets]
+    K, W = args.steps, args.warmup
+
+    def launch(i):
+        s = sets[i % nsets]
+        return fem.energy_loss_and_grad(s["u"], **kws[i % nsets])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (eager), then capture K steps into one CUDA graph
+    for i in range(max(W, 3)):
+        out = launch(i)
+    torch.cuda.synchronize()
+    mode = "cuda_graph"
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(2):
+                    launch(i)                      # allocate this stream's workspace before capture
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(K):
+                    launch(i)                      # outputs are recycled by the graph's pool
+            graph.replay()                         # one untimed replay
+            torch.cuda.synchronize()
+        except Exception as e:   # noqa: BLE001
+            graph, mode = None, f"eager (graph capture failed: {type(e).__name__})"
+            torch.cuda.synchronize()
+    else:
+        mode = "eager"
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = args.reps
+    times = []
+    for _ in range(reps):
+        barrier()
+        e0.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(K):
+                launch(i)
+        e1.record()
+        barrier()
+        times.append(e0.elapsed_time(e1))
+    ms_total = sorted(times)[len(times) // 2]      # median repetition of the K-step region
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = dof_step * world / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e: public API, pinned host inputs, H2D + launch + D2H(loss) every step
+    hs = sets[0]
+    host = [f.detach().cpu().pin_memory() for f in hs["_fields"]]
+    devbuf = [torch.empty_like(f) for f in hs["_fields"]]
+    h2d = sum(h.numel() * h.element_size() for h in host)
+
+    def rebuild(fields):
+        if nsd == 2:
+            u, inputs, f = fields
+            return u, dict(nu=inputs[:, 0:1], f=f, dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)])
+        kw = dict(call_kwargs(hs))
+        ordered = [t for t in hs["_fields"]]
+        remap = {id(o): n for o, n in zip(ordered, fields)}
+        def m(x):
+            return remap.get(id(x), x)
+        kw = {k: (m(v) if torch.is_tensor(v) else ([(m(a), b) for a, b in v] if k == "dirichlet" else v))
+              for k, v in kw.items()}
+        return m(hs["u"]), kw
+
+    def e2e_step():
+        for h, d in zip(host, devbuf):
+            d.copy_(h, non_blocking=True)
+        u, kw = rebuild(devbuf)
+        loss, grad = fem.energy_loss_and_grad(u, **kw)
+        return float(loss)                          # D2H read of the step's result (syncs)
+
+    for _ in range(3):
+        e2e_step()
+    Ke = max(3, min(K, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = dof_step * world * Ke / float(te.item()) / 1e9
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = step_bytes / (ms_step * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            sB = cpu_sample_batch(name)
+            best, dof = oracle_step_time(name, sB, threads)
+            cpu = {"value": dof / best / 1e9, "unit": "GDOF/s", "cores": threads, "kind": "port",
+                   "sample": f"oracle fwd+bwd on B={sB} of {B} samples ({dof} DOF), best of 3, torch {torch.__version__} CPU"}
+        line = {
+            "metric": "FEM loss+grad throughput", "value": value, "unit": "GDOF/s", "n_gpus": world,
+            "steps": K, "warmup": max(W, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "desc": desc, "batch_per_gpu": B, "grid": [size] * nsd,
+                       "dof_per_step_per_gpu": dof_step, "launch": mode,
+                       "l2": f"inputs rotated over {nsets} buffer sets ({nsets * step_bytes / 1e6:.0f} MB > 126 MB L2)",
+                       "timing": f"CUDA events around {K} steps, median of {reps} repetitions, max over ranks",
+                       "parallelism": f"dp{world} (batch sharded, no data-path collective)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_dof": bpd, "kernel": "k_fem2d" if nsd == 2 else "k_fem3d"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "steps": Ke, "note": "pinned host -> device copy of all input fields + fused launch + loss.item()"},
+            "gpu_launches": K,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

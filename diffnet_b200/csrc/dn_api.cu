@@ -1,0 +1,387 @@
+// dn_api.cu -- extern "C" entry points of libdiffnet_fem.so (see include/diffnet_fem.h).
+// Validation, constant folding, launch planning and template dispatch; no device state.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "dn_common.cuh"
+#include "fem2d.cuh"
+#include "fem3d.cuh"
+#include "gp_eval.cuh"
+
+namespace dn {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return DN_OK;
+  return fail(DN_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+// One device query per process and device.
+struct DevInfo { int checked, ok, sms; };
+static DevInfo g_dev[64];
+
+static int device_ok(int* sms) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return check_cuda(e, "cudaGetDevice");
+  if (dev < 0 || dev >= 64) return fail(DN_EINVAL, "device index %d out of range", dev);
+  if (!g_dev[dev].checked) {
+    int major = 0, minor = 0, n = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_dev[dev].ok = (major == 10 && minor == 0);
+    g_dev[dev].sms = n;
+    g_dev[dev].checked = 1;
+    if (!g_dev[dev].ok)
+      return fail(DN_EARCH, "device %d is sm_%d%d; libdiffnet_fem is built for sm_100a (B200) only",
+                  dev, major, minor);
+  }
+  if (!g_dev[dev].ok) return fail(DN_EARCH, "device %d is not sm_100", dev);
+  if (sms) *sms = g_dev[dev].sms;
+  return DN_OK;
+}
+
+// 1-D Gauss rules with the reference's own (truncated) constants, DiffNetFEM.py:128-141.
+static int gauss_rule(int n, double* x, double* w) {
+  switch (n) {
+    case 2: x[0] = -0.5773502691896258; x[1] = 0.5773502691896258; w[0] = w[1] = 1.0; return 0;
+    case 3: x[0] = -0.774596669; x[1] = 0.0; x[2] = 0.774596669;
+            w[0] = 5.0 / 9.0; w[1] = 8.0 / 9.0; w[2] = 5.0 / 9.0; return 0;
+    case 4: x[0] = -0.861136; x[1] = -0.339981; x[2] = 0.339981; x[3] = 0.861136;
+            w[0] = 0.347855; w[1] = 0.652145; w[2] = 0.652145; w[3] = 0.347855; return 0;
+  }
+  return -1;
+}
+
+static Field to_field(const dn_field* f) {
+  Field o{nullptr, 0, 0, 0};
+  if (f && f->ptr) { o.p = f->ptr; o.sb = f->stride_b; o.sz = f->stride_z; o.sy = f->stride_y; }
+  return o;
+}
+
+static bool aligned4(const Field& f, bool use_z) {
+  if (!f.p) return true;
+  return ((uintptr_t)f.p % 16 == 0) && (f.sb % 4 == 0) && (f.sy % 4 == 0) && (!use_z || f.sz % 4 == 0);
+}
+
+struct Common {
+  Field u, nu, f, fgp, numask;
+  Mask mk[DN_MAX_MASKS];
+  int nmasks, MK;
+  Consts k;
+  Rule rule;
+  bool vec4;
+};
+
+static int prepare(const dn_field* u, const dn_field* nu, const dn_field* f, const dn_field* fgp,
+                   const dn_mask* masks, int nmasks, const dn_field* nu_zero_mask,
+                   const dn_geom* g, double c_k, double c_f, double S, int nsd, Common* c) {
+  if (!g) return fail(DN_EINVAL, "geom is NULL");
+  if (g->nsd != nsd) return fail(DN_EINVAL, "geom.nsd=%d but the %d-D entry point was called", g->nsd, nsd);
+  if (g->batch < 1 || g->nx < 2 || g->ny < 2 || (nsd == 3 && g->nz < 2))
+    return fail(DN_EINVAL, "need batch >= 1 and >= 2 nodes per direction (B=%d nx=%d ny=%d nz=%d)",
+                g->batch, g->nx, g->ny, g->nz);
+  if (!(g->hx > 0) || !(g->hy > 0) || (nsd == 3 && !(g->hz > 0)))
+    return fail(DN_EINVAL, "element sizes must be positive");
+  if (!u || !u->ptr) return fail(DN_EINVAL, "u is NULL");
+  if (f && f->ptr && fgp && fgp->ptr) return fail(DN_EINVAL, "give f or fgp, not both");
+  if (nmasks < 0 || nmasks > DN_MAX_MASKS)
+    return fail(DN_EINVAL, "nmasks=%d (max %d)", nmasks, DN_MAX_MASKS);
+  if (nmasks > 0 && !masks) return fail(DN_EINVAL, "masks is NULL");
+  double gx[4], gw[4];
+  if (gauss_rule(g->ngp_1d, gx, gw)) return fail(DN_EINVAL, "ngp_1d=%d (2..4)", g->ngp_1d);
+
+  c->u = to_field(u); c->nu = to_field(nu); c->f = to_field(f); c->fgp = to_field(fgp);
+  c->numask = to_field(nu_zero_mask);
+  if (c->numask.p && !c->nu.p) return fail(DN_EINVAL, "nu_zero_mask needs nu");
+  c->nmasks = nmasks;
+  int nvf = 0;
+  for (int i = 0; i < DN_MAX_MASKS; ++i) c->mk[i] = Mask{{nullptr, 0, 0, 0}, {nullptr, 0, 0, 0}, 0.f};
+  for (int i = 0; i < nmasks; ++i) {
+    if (!masks[i].mask.ptr) return fail(DN_EINVAL, "masks[%d].mask is NULL", i);
+    c->mk[i].m = to_field(&masks[i].mask);
+    c->mk[i].vf = to_field(&masks[i].value_field);
+    c->mk[i].v = masks[i].value;
+    nvf += c->mk[i].vf.p ? 1 : 0;
+  }
+  if (nvf > 0 && nmasks != 1)
+    return fail(DN_EINVAL, "a Dirichlet value_field is supported only as the single mask");
+  c->MK = nvf ? 4 : nmasks;
+
+  // rule moments: W1 = sum w, t = sum w x^2 / W1
+  double W1 = 0, m2 = 0;
+  for (int i = 0; i < g->ngp_1d; ++i) { W1 += gw[i]; m2 += gw[i] * gx[i] * gx[i]; }
+  const double t = m2 / W1;
+  const double Wn = (nsd == 2) ? W1 * W1 : W1 * W1 * W1;
+  const double nrm = (nsd == 2) ? 64.0 : 512.0;     // (2^nsd)^2 from un-normalised C * A^2
+  c->k.kx = (float)(S * c_k * Wn * (2.0 / g->hx) * (2.0 / g->hx) / nrm);
+  c->k.ky = (float)(S * c_k * Wn * (2.0 / g->hy) * (2.0 / g->hy) / nrm);
+  c->k.kz = (nsd == 3) ? (float)(S * c_k * Wn * (2.0 / g->hz) * (2.0 / g->hz) / nrm) : 0.f;
+  c->k.kf = (float)(S * c_f * Wn / ((nsd == 2) ? 16.0 : 64.0));
+  c->k.t = (float)t;
+  c->rule.n = g->ngp_1d;
+  for (int i = 0; i < 4; ++i) {
+    c->rule.x[i] = i < g->ngp_1d ? (float)gx[i] : 0.f;
+    c->rule.w[i] = i < g->ngp_1d ? (float)gw[i] : 0.f;
+  }
+  c->rule.fscale = (float)(((nsd == 2) ? 4.0 : 8.0) / Wn);
+
+  bool v4 = (g->nx % 4 == 0);
+  const bool z = (nsd == 3);
+  v4 = v4 && aligned4(c->u, z) && aligned4(c->nu, z) && aligned4(c->f, z) && aligned4(c->numask, z);
+  for (int i = 0; i < nmasks; ++i) v4 = v4 && aligned4(c->mk[i].m, z) && aligned4(c->mk[i].vf, z);
+  if (env_int("DN_FORCE_SCALAR", 0)) v4 = false;
+  c->vec4 = v4;
+  return DN_OK;
+}
+
+// ------------------------------------------------------------------------------------ 2-D
+struct Plan2D { int V, R, nchunks, ntx, nitems, wpc, grid; };
+
+static Plan2D plan2d(const dn_geom* g, bool vec4, int sms) {
+  Plan2D pl;
+  pl.V = vec4 ? 4 : 1;
+  pl.ntx = (g->nx + 32 * pl.V - 1) / (32 * pl.V);
+  // enough warps to give every SM ~16, but chunks of at least 8 rows (halo rows are re-read
+  // from L2 and their elements recomputed: (R+1)/R work, (R+2)/R loads)
+  const long long target = (long long)sms * env_int("DN_WARPS_PER_SM_2D", 16);
+  long long per_row_items = (long long)g->batch * pl.ntx;
+  long long want = (target + per_row_items - 1) / per_row_items;
+  if (want < 1) want = 1;
+  int R = (int)((g->ny + want - 1) / want);
+  const int Rmin = env_int("DN_RMIN_2D", 8);
+  if (R < Rmin) R = Rmin;
+  if (R > g->ny) R = g->ny;
+  R = env_int("DN_R_2D", R);
+  pl.R = R;
+  pl.nchunks = (g->ny + R - 1) / R;
+  pl.nitems = g->batch * pl.nchunks * pl.ntx;
+  pl.wpc = env_int("DN_WPC_2D", pl.ntx == 2 ? 2 : 4);
+  pl.grid = (pl.nitems + pl.wpc - 1) / pl.wpc;
+  return pl;
+}
+
+static size_t ws_bytes_for_grid(long long grid) { return 64 + 8 * (size_t)grid; }
+
+static int run2d(const Common& c, const dn_geom* g, float* grad, float* grad_nu, int mode,
+                 int mask_input, void* workspace, size_t wsb, double* loss_out, float* loss_f32,
+                 void* stream, int sms) {
+  bool vec4 = c.vec4 && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)grad_nu % 16 == 0);
+  Plan2D pl = plan2d(g, vec4, sms);
+  if (!workspace || wsb < ws_bytes_for_grid(pl.grid))
+    return fail(DN_EWORKSPACE, "workspace too small: %zu < %zu", wsb, ws_bytes_for_grid(pl.grid));
+  if ((uintptr_t)workspace % 16) return fail(DN_EWORKSPACE, "workspace must be 16-byte aligned");
+  P2D p;
+  memset(&p, 0, sizeof(p));
+  p.u = c.u; p.nu = c.nu; p.f = c.f; p.fgp = c.fgp; p.numask = c.numask;
+  for (int i = 0; i < DN_MAX_MASKS; ++i) p.mk[i] = c.mk[i];
+  p.B = g->batch; p.nx = g->nx; p.ny = g->ny;
+  p.k = c.k; p.rule = c.rule;
+  p.R = pl.R; p.nchunks = pl.nchunks; p.ntx = pl.ntx; p.nitems = pl.nitems;
+  p.grad = grad; p.grad_nu = grad_nu;
+  p.red.counter = (unsigned int*)workspace;
+  p.red.partials = (double*)((char*)workspace + 64);
+  p.red.loss_out = loss_out; p.red.loss_f32 = loss_f32;
+  p.mode = mode; p.mask_input = mask_input;
+  const int FM = c.f.p ? 1 : (c.fgp.p ? 2 : 0);
+  launch2d_fn fn = get_launch2d(pl.V, c.MK, c.nu.p ? 1 : 0, FM, c.numask.p ? 1 : 0, grad_nu ? 1 : 0);
+  if (!fn)
+    return fail(DN_EINVAL, "unsupported option combination (V=%d MK=%d nu=%d fmode=%d numask=%d grad_nu=%d)",
+                pl.V, c.MK, c.nu.p ? 1 : 0, FM, c.numask.p ? 1 : 0, grad_nu ? 1 : 0);
+  return check_cuda(fn(p, dim3(pl.grid), dim3(32 * pl.wpc), (cudaStream_t)stream), "fem2d launch");
+}
+
+}  // namespace dn
+
+using namespace dn;
+
+extern "C" {
+
+int dn_abi_version(void) { return DN_ABI_VERSION; }
+const char* dn_last_error(void) { return g_err; }
+int dn_device_check(void) { return device_ok(nullptr); }
+
+size_t dn_fem_workspace_bytes(const dn_geom* g) {
+  if (!g) return 0;
+  // upper bound over both lane widths and any env override; grids are <= items
+  int sms = 148;
+  long long worst = 0;
+  if (g->nsd == 2) {
+    for (int v = 0; v < 2; ++v) {
+      Plan2D pl = plan2d(g, v == 1, sms);
+      if (pl.nitems > worst) worst = pl.nitems;
+    }
+  } else {
+    worst = plan3d_max_ctas(g);
+  }
+  return ws_bytes_for_grid(worst + 1024);
+}
+
+int dn_fem_energy_2d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                         const dn_field* fgp, const dn_mask* masks, int nmasks,
+                         const dn_field* nu_zero_mask, const dn_geom* g, const dn_consts* c,
+                         float* grad_u, float* grad_nu, void* workspace, size_t workspace_bytes,
+                         double* loss_out, float* loss_out_f32, void* stream) {
+  int sms = 0;
+  if (int rc = device_ok(&sms)) return rc;
+  if (!c) return fail(DN_EINVAL, "consts is NULL");
+  if (!g) return fail(DN_EINVAL, "geom is NULL");
+  const double count = (c->reduction == 0)
+      ? (g->mean_count > 0 ? g->mean_count : (double)g->batch * (g->nx - 1) * (double)(g->ny - 1))
+      : 1.0;
+  Common cm;
+  if (int rc = prepare(u, nu, f, fgp, masks, nmasks, nu_zero_mask, g, c->c_k, c->c_f,
+                       c->scale / count, 2, &cm)) return rc;
+  if (grad_nu && !cm.nu.p) return fail(DN_EINVAL, "grad_nu requested without nu");
+  return run2d(cm, g, grad_u, grad_nu, 0, 1, workspace, workspace_bytes, loss_out, loss_out_f32,
+               stream, sms);
+}
+
+int dn_fem_residual_2d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                           const dn_mask* masks, int nmasks, int apply_masks_to_input,
+                           const dn_geom* g, double jac, float* residual, void* workspace,
+                           size_t workspace_bytes, double* loss_out, float* loss_out_f32,
+                           void* stream) {
+  int sms = 0;
+  if (int rc = device_ok(&sms)) return rc;
+  if (!residual) return fail(DN_EINVAL, "residual output is NULL");
+  Common cm;
+  // R = d/du [ sum_e sum_g jac w_g ( 1/2 nu |grad u|^2 - u f ) ]
+  if (int rc = prepare(u, nu, f, nullptr, masks, nmasks, nullptr, g, 0.5 * jac, jac, 1.0, 2, &cm))
+    return rc;
+  return run2d(cm, g, residual, nullptr, 1, apply_masks_to_input ? 1 : 0, workspace,
+               workspace_bytes, loss_out, loss_out_f32, stream, sms);
+}
+
+int dn_fem_energy_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                         const dn_field* fgp, const dn_mask* masks, int nmasks,
+                         const dn_field* nu_zero_mask, const dn_geom* g, const dn_consts* c,
+                         float* grad_u, float* grad_nu, void* workspace, size_t workspace_bytes,
+                         double* loss_out, float* loss_out_f32, void* stream) {
+  int sms = 0;
+  if (int rc = device_ok(&sms)) return rc;
+  if (!c) return fail(DN_EINVAL, "consts is NULL");
+  if (!g) return fail(DN_EINVAL, "geom is NULL");
+  if (grad_nu) return fail(DN_EINVAL, "grad_nu is not implemented for 3-D");
+  double count = 1.0;
+  if (c->reduction == 0) {
+    long long nelz = g->nz - 1;
+    if (g->z_own_hi > g->z_own_lo) {
+      const int hi = g->z_own_hi < g->nz - 1 ? g->z_own_hi : g->nz - 1;
+      nelz = hi - g->z_own_lo;
+    }
+    count = g->mean_count > 0 ? g->mean_count
+                              : (double)g->batch * (g->nx - 1) * (double)(g->ny - 1) * (double)nelz;
+  }
+  Common cm;
+  if (int rc = prepare(u, nu, f, fgp, masks, nmasks, nu_zero_mask, g, c->c_k, c->c_f,
+                       c->scale / count, 3, &cm)) return rc;
+  return run3d(cm.u, cm.nu, cm.f, cm.fgp, cm.numask, cm.mk, cm.MK, cm.k, cm.rule, cm.vec4, g,
+               grad_u, 0, 1, workspace, workspace_bytes, loss_out, loss_out_f32, stream, sms);
+}
+
+int dn_fem_residual_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                           const dn_mask* masks, int nmasks, int apply_masks_to_input,
+                           const dn_geom* g, double jac, float* residual, void* workspace,
+                           size_t workspace_bytes, double* loss_out, float* loss_out_f32,
+                           void* stream) {
+  int sms = 0;
+  if (int rc = device_ok(&sms)) return rc;
+  if (!residual) return fail(DN_EINVAL, "residual output is NULL");
+  Common cm;
+  if (int rc = prepare(u, nu, f, nullptr, masks, nmasks, nullptr, g, 0.5 * jac, jac, 1.0, 3, &cm))
+    return rc;
+  return run3d(cm.u, cm.nu, cm.f, cm.fgp, cm.numask, cm.mk, cm.MK, cm.k, cm.rule, cm.vec4, g,
+               residual, 1, apply_masks_to_input ? 1 : 0, workspace, workspace_bytes, loss_out,
+               loss_out_f32, stream, sms);
+}
+
+static int gp_common(const dn_geom* g, int which, int nsd, GpTables* tb) {
+  if (!g) return fail(DN_EINVAL, "geom is NULL");
+  if (g->nsd != nsd) return fail(DN_EINVAL, "geom.nsd mismatch");
+  if (g->batch < 1 || g->nx < 2 || g->ny < 2 || (nsd == 3 && g->nz < 2))
+    return fail(DN_EINVAL, "need >= 2 nodes per direction");
+  if (which < 0 || which > (nsd == 2 ? 2 : 3)) return fail(DN_EINVAL, "which=%d", which);
+  double gx[4], gw[4];
+  if (gauss_rule(g->ngp_1d, gx, gw)) return fail(DN_EINVAL, "ngp_1d=%d (2..4)", g->ngp_1d);
+  // 1-D factors per Gauss point: value table N1[gp][bf] and derivative table D1[bf] * (2/h).
+  // The reference stores the fp32 rounding of the f64 product including 2/h
+  // (DiffNetFEM.py:198-215, 405-453); the separable evaluation here agrees to 1 ulp-ish.
+  tb->n = g->ngp_1d;
+  const double s[3] = {2.0 / g->hx, 2.0 / g->hy, nsd == 3 ? 2.0 / g->hz : 0.0};
+  for (int d = 0; d < 3; ++d) {
+    const bool der = (which == d + 1);
+    for (int q = 0; q < 4; ++q) {
+      const double x = q < g->ngp_1d ? gx[q] : 0.0;
+      tb->c[d][q][0] = (float)(der ? -0.5 * s[d] : 0.5 * (1.0 - x));
+      tb->c[d][q][1] = (float)(der ? +0.5 * s[d] : 0.5 * (1.0 + x));
+    }
+  }
+  return DN_OK;
+}
+
+int dn_fem_gp_eval_2d_f32(const dn_field* in, const dn_geom* g, int which, float* out,
+                          void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  GpTables tb;
+  if (int rc = gp_common(g, which, 2, &tb)) return rc;
+  if (!in || !in->ptr || !out) return fail(DN_EINVAL, "NULL input/output");
+  return check_cuda(launch_gp_eval(to_field(in), g->batch, g->nx, g->ny, 1, 2, tb, out,
+                                   (cudaStream_t)stream), "gp_eval launch");
+}
+
+int dn_fem_gp_eval_3d_f32(const dn_field* in, const dn_geom* g, int which, float* out,
+                          void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  GpTables tb;
+  if (int rc = gp_common(g, which, 3, &tb)) return rc;
+  if (!in || !in->ptr || !out) return fail(DN_EINVAL, "NULL input/output");
+  return check_cuda(launch_gp_eval(to_field(in), g->batch, g->nx, g->ny, g->nz, 3, tb, out,
+                                   (cudaStream_t)stream), "gp_eval launch");
+}
+
+int dn_fem_gp_eval_adj_2d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in,
+                              void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  GpTables tb;
+  if (int rc = gp_common(g, which, 2, &tb)) return rc;
+  if (!grad_out || !grad_in) return fail(DN_EINVAL, "NULL input/output");
+  return check_cuda(launch_gp_eval_adj(grad_out, g->batch, g->nx, g->ny, 1, 2, tb, grad_in,
+                                       (cudaStream_t)stream), "gp_eval_adj launch");
+}
+
+int dn_fem_gp_eval_adj_3d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in,
+                              void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  GpTables tb;
+  if (int rc = gp_common(g, which, 3, &tb)) return rc;
+  if (!grad_out || !grad_in) return fail(DN_EINVAL, "NULL input/output");
+  return check_cuda(launch_gp_eval_adj(grad_out, g->batch, g->nx, g->ny, g->nz, 3, tb, grad_in,
+                                       (cudaStream_t)stream), "gp_eval_adj launch");
+}
+
+int dn_scale_inplace_f32(float* x, size_t n, const float* factor_dev, void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!x || !factor_dev) return fail(DN_EINVAL, "NULL pointer");
+  if (n == 0) return DN_OK;
+  return check_cuda(launch_scale(x, n, factor_dev, (cudaStream_t)stream), "scale launch");
+}
+
+}  // extern "C"

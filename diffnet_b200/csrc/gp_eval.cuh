@@ -1,0 +1,23 @@
+// gp_eval.cuh -- standalone Gauss-point evaluation (gauss_pt_eval, DiffNet/DiffNetFEM.py:7-18)
+// and its adjoint (autograd's convolution_backward w.r.t. the input), plus the in-place
+// gradient scaling used by the autograd wrapper.  Generic in ngp_1d (2..4); these serve
+// user-written loss() bodies that are not one of the fused forms.
+#pragma once
+#include "dn_common.cuh"
+
+namespace dn {
+
+// 1-D factors: c[d][q][a] for direction d (0=x,1=y,2=z), Gauss point q, basis function a:
+// shape-function value, or derivative*(2/h) for the differentiated direction.
+struct GpTables {
+  int n;
+  float c[3][4][2];
+};
+
+cudaError_t launch_gp_eval(Field in, int B, int nx, int ny, int nz, int nsd, const GpTables& tb,
+                           float* out, cudaStream_t s);
+cudaError_t launch_gp_eval_adj(const float* gout, int B, int nx, int ny, int nz, int nsd,
+                               const GpTables& tb, float* gin, cudaStream_t s);
+cudaError_t launch_scale(float* x, size_t n, const float* factor_dev, cudaStream_t s);
+
+}  // namespace dn

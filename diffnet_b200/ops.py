@@ -1,0 +1,361 @@
+"""torch.autograd.Function wrappers over the C ABI (the drop-in seam for DiffNet's loss()).
+
+  fem_energy(...)    fused Poisson energy loss, differentiable w.r.t. u (and nu in 2-D)
+  fem_residual(...)  assembled-residual loss  sum(R^2), differentiable w.r.t. u
+  gp_eval(...)       gauss_pt_evaluation{,_der_x,_der_y,_der_z}, differentiable w.r.t. its input
+
+Everything runs on the CUDA stream torch considers current; there is no host sync inside and no
+CPU path (CPU tensors raise).  See include/diffnet_fem.h for the C side.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+@dataclass(frozen=True)
+class Geometry:
+    """Mesh description shared by every call (mirrors the reference's kwargs -> attributes,
+    DiffNet/base.py:16-32, DiffNetFEM.py:42-51)."""
+    nsd: int
+    nx: int
+    ny: int
+    nz: int
+    hx: float
+    hy: float
+    hz: float
+    ngp_1d: int = 2
+
+    @property
+    def spatial(self) -> Tuple[int, ...]:
+        return (self.ny, self.nx) if self.nsd == 2 else (self.nz, self.ny, self.nx)
+
+    @property
+    def elems(self) -> Tuple[int, ...]:
+        return tuple(s - 1 for s in self.spatial)
+
+
+# ------------------------------------------------------------------------------ marshalling
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise L.DiffNetFEMError(
+            f"{name} is on {t.device}: the FEM ops are CUDA (sm_100a) only, there is no CPU fallback")
+
+
+def _canon(t: torch.Tensor, geom: Geometry, name: str) -> torch.Tensor:
+    """View `t` as (Bt, *spatial) with x contiguous, fp32.  Accepted layouts: bare spatial,
+    (B, *spatial) and (B, 1, *spatial) -- what the reference's where()/conv broadcasting accepts
+    (solve_in_object_3d.py:198-199 passes a bare (D,H,W) parameter)."""
+    _require_cuda(t, name)
+    sp = geom.spatial
+    nsd = geom.nsd
+    if t.dtype != torch.float32:
+        if t.dtype in (torch.bool, torch.uint8):
+            t = t.to(torch.float32)
+        else:
+            raise L.DiffNetFEMError(f"{name} must be float32 (got {t.dtype})")
+    if t.dim() == nsd + 2:
+        if t.shape[1] != 1:
+            raise L.DiffNetFEMError(f"{name}: expected one channel, got shape {tuple(t.shape)}")
+        t = t[:, 0]
+    elif t.dim() == nsd:
+        t = t.unsqueeze(0)
+    elif t.dim() != nsd + 1:
+        raise L.DiffNetFEMError(f"{name}: bad shape {tuple(t.shape)} for a {nsd}-D nodal field")
+    if tuple(t.shape[1:]) != sp:
+        raise L.DiffNetFEMError(f"{name}: spatial shape {tuple(t.shape[1:])} != mesh nodes {sp}")
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _field(t: Optional[torch.Tensor], B: int, nsd: int) -> L.dn_field:
+    if t is None:
+        return L.dn_field(None, 0, 0, 0)
+    bt = t.shape[0]
+    if bt != B and bt != 1:
+        raise L.DiffNetFEMError(f"batch {bt} does not broadcast to {B}")
+    sb = t.stride(0) if (bt == B and B > 1) else 0
+    if nsd == 2:
+        return L.dn_field(t.data_ptr(), sb, 0, t.stride(1))
+    return L.dn_field(t.data_ptr(), sb, t.stride(1), t.stride(2))
+
+
+def _geom_struct(geom: Geometry, B: int, z_own=None, mean_count=0.0) -> L.dn_geom:
+    zo = z_own or (0, 0)
+    return L.dn_geom(geom.nsd, B, geom.nx, geom.ny, geom.nz if geom.nsd == 3 else 1, geom.ngp_1d,
+                     geom.hx, geom.hy, geom.hz if geom.nsd == 3 else 0.0, int(zo[0]), int(zo[1]),
+                     float(mean_count))
+
+
+_workspaces = {}
+
+
+def _workspace(device: torch.device, stream_ptr: int, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch (ticket counter + per-CTA partials), one per device and stream;
+    the kernels leave it ready for the next call."""
+    key = (device.index, stream_ptr)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _masks_struct(dirichlet, geom: Geometry, B: int, keep):
+    n = len(dirichlet)
+    if n > L.DN_MAX_MASKS:
+        raise L.DiffNetFEMError(f"at most {L.DN_MAX_MASKS} Dirichlet conditions per call (got {n})")
+    arr = (L.dn_mask * max(n, 1))()
+    for i, (mask, value) in enumerate(dirichlet):
+        m = _canon(mask, geom, f"dirichlet[{i}].mask")
+        keep.append(m)
+        arr[i].mask = _field(m, B, geom.nsd)
+        if torch.is_tensor(value):
+            v = _canon(value, geom, f"dirichlet[{i}].value")
+            keep.append(v)
+            arr[i].value_field = _field(v, B, geom.nsd)
+            arr[i].value = 0.0
+        else:
+            arr[i].value_field = L.dn_field(None, 0, 0, 0)
+            arr[i].value = float(value)
+    return arr, n
+
+
+def _batch_of(*ts) -> int:
+    B = 1
+    for t in ts:
+        if t is not None:
+            B = max(B, t.shape[0])
+    return B
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def energy_raw(geom: Geometry, u, nu=None, f=None, f_gp=None, dirichlet=(), nu_zero_mask=None,
+               c_k=1.0, c_f=1.0, scale=1.0, reduction="mean", want_grad=True, want_grad_nu=False,
+               z_own=None, mean_count=0.0, want_double=False):
+    """One fused launch.  Returns (loss 0-dim fp32, grad_u (B,*spatial) or None,
+    grad_nu or None[, loss fp64 0-dim])."""
+    keep = []
+    uc = _canon(u, geom, "u")
+    nuc = _canon(nu, geom, "nu") if nu is not None else None
+    fc = _canon(f, geom, "f") if f is not None else None
+    nzm = _canon(nu_zero_mask, geom, "nu_zero_mask") if nu_zero_mask is not None else None
+    fg = None
+    if f_gp is not None:
+        _require_cuda(f_gp, "f_gp")
+        ngp = geom.ngp_1d ** geom.nsd
+        fg = f_gp if f_gp.dim() == geom.nsd + 2 else f_gp.unsqueeze(0)
+        if tuple(fg.shape[1:]) != (ngp,) + geom.elems or fg.dtype != torch.float32:
+            raise L.DiffNetFEMError(
+                f"f_gp must be float32 (B|1, {ngp}, {geom.elems}); got {tuple(f_gp.shape)} {f_gp.dtype}")
+        fg = fg.contiguous()
+    masks_t = [m for m, _ in dirichlet] + [v for _, v in dirichlet if torch.is_tensor(v)]
+    B = _batch_of(uc, nuc, fc, nzm, fg, *[_canon(m, geom, "mask") for m in masks_t])
+    marr, nm = _masks_struct(dirichlet, geom, B, keep)
+    dev = uc.device
+    g = _geom_struct(geom, B, z_own, mean_count)
+    cs = L.dn_consts(float(c_k), float(c_f), float(scale), 0 if reduction == "mean" else 1, 0)
+    if reduction not in ("mean", "sum"):
+        raise L.DiffNetFEMError("reduction must be 'mean' or 'sum'")
+    grad = torch.empty((B,) + geom.spatial, dtype=torch.float32, device=dev) if want_grad else None
+    grad_nu = torch.empty((B,) + geom.spatial, dtype=torch.float32, device=dev) if want_grad_nu else None
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    loss64 = torch.empty((), dtype=torch.float64, device=dev) if want_double else None
+    lib = L.lib()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, stream, lib.dn_fem_workspace_bytes(C.byref(g)))
+        fu, fnu, ff = _field(uc, B, geom.nsd), _field(nuc, B, geom.nsd), _field(fc, B, geom.nsd)
+        ffg = L.dn_field(None, 0, 0, 0)
+        if fg is not None:
+            ffg = L.dn_field(fg.data_ptr(), fg.stride(0) if (fg.shape[0] == B and B > 1) else 0, 0, 0)
+        fnz = _field(nzm, B, geom.nsd)
+        fn = lib.dn_fem_energy_2d_f32 if geom.nsd == 2 else lib.dn_fem_energy_3d_f32
+        rc = fn(C.byref(fu), C.byref(fnu) if nuc is not None else None,
+                C.byref(ff) if fc is not None else None, C.byref(ffg) if fg is not None else None,
+                marr, nm, C.byref(fnz) if nzm is not None else None, C.byref(g), C.byref(cs),
+                _ptr(grad), _ptr(grad_nu), C.c_void_p(ws.data_ptr()), ws.numel(), _ptr(loss64),
+                _ptr(loss), C.c_void_p(stream))
+    L.check(rc, f"dn_fem_energy_{geom.nsd}d_f32")
+    out = (loss, grad, grad_nu)
+    return out + (loss64,) if want_double else out
+
+
+def residual_raw(geom: Geometry, u, nu=None, f=None, dirichlet=(), jac=1.0, apply_masks_to_input=True):
+    """R = jac*(K(nu) u' - F(f)) masked, and sum(R^2).  Returns (loss 0-dim, R (B,*spatial))."""
+    keep = []
+    uc = _canon(u, geom, "u")
+    nuc = _canon(nu, geom, "nu") if nu is not None else None
+    fc = _canon(f, geom, "f") if f is not None else None
+    B = _batch_of(uc, nuc, fc, *[_canon(m, geom, "mask") for m, _ in dirichlet])
+    marr, nm = _masks_struct(dirichlet, geom, B, keep)
+    dev = uc.device
+    g = _geom_struct(geom, B)
+    R = torch.empty((B,) + geom.spatial, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    lib = L.lib()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, stream, lib.dn_fem_workspace_bytes(C.byref(g)))
+        fu, fnu, ff = _field(uc, B, geom.nsd), _field(nuc, B, geom.nsd), _field(fc, B, geom.nsd)
+        fn = lib.dn_fem_residual_2d_f32 if geom.nsd == 2 else lib.dn_fem_residual_3d_f32
+        rc = fn(C.byref(fu), C.byref(fnu) if nuc is not None else None,
+                C.byref(ff) if fc is not None else None, marr, nm, 1 if apply_masks_to_input else 0,
+                C.byref(g), float(jac), _ptr(R), C.c_void_p(ws.data_ptr()), ws.numel(), None,
+                _ptr(loss), C.c_void_p(stream))
+    L.check(rc, f"dn_fem_residual_{geom.nsd}d_f32")
+    return loss, R
+
+
+def scale_inplace_(x: torch.Tensor, factor: torch.Tensor) -> torch.Tensor:
+    """x *= factor (0-dim device tensor), free when factor == 1 (checked on the device)."""
+    _require_cuda(x, "x")
+    assert x.is_contiguous() and x.dtype == torch.float32
+    fac = factor.detach().to(device=x.device, dtype=torch.float32).reshape(())
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        rc = L.lib().dn_scale_inplace_f32(C.c_void_p(x.data_ptr()), x.numel(),
+                                          C.c_void_p(fac.data_ptr()), C.c_void_p(stream))
+    L.check(rc, "dn_scale_inplace_f32")
+    return x
+
+
+def _like_input(grad_b: torch.Tensor, ref: torch.Tensor, geom: Geometry) -> torch.Tensor:
+    """Reduce/reshape a dense (B,*spatial) gradient to the shape of the tensor the user passed."""
+    if ref.dim() == geom.nsd:                       # bare field broadcast over the batch
+        return grad_b.sum(0) if grad_b.shape[0] > 1 else grad_b[0]
+    bt = ref.shape[0]
+    g = grad_b
+    if bt == 1 and g.shape[0] > 1:
+        g = g.sum(0, keepdim=True)
+    return g.reshape(ref.shape)
+
+
+# ------------------------------------------------------------------------------ autograd
+class FEMEnergyFunction(torch.autograd.Function):
+    """loss = energy(u, nu, ...); backward returns grad_output * dloss/du (and dloss/dnu).
+
+    Forward AND gradient come from the single fused launch in forward(); backward only scales
+    (in place, skipped on the device when grad_output == 1).  First-order only
+    (once_differentiable), which is all Adam / LBFGS need."""
+
+    @staticmethod
+    def forward(ctx, u, nu, geom, f, f_gp, dirichlet, nu_zero_mask, c_k, c_f, scale, reduction,
+                z_own, mean_count):
+        need_u = ctx.needs_input_grad[0]
+        need_nu = nu is not None and ctx.needs_input_grad[1]
+        loss, grad, grad_nu = energy_raw(
+            geom, u.detach(), None if nu is None else nu.detach(), f, f_gp, dirichlet,
+            nu_zero_mask, c_k, c_f, scale, reduction, want_grad=need_u or need_nu,
+            want_grad_nu=need_nu, z_own=z_own, mean_count=mean_count)
+        ctx.geom = geom
+        ctx.u_ref = u if need_u else None
+        ctx.nu_ref = nu if need_nu else None
+        ctx.save_for_backward(*[t for t in (grad if need_u else None, grad_nu) if t is not None])
+        ctx.has = (need_u, need_nu)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        saved = list(ctx.saved_tensors)
+        gu = gnu = None
+        if ctx.has[0]:
+            gu = _like_input(scale_inplace_(saved.pop(0), gout), ctx.u_ref, ctx.geom)
+        if ctx.has[1]:
+            gnu = _like_input(scale_inplace_(saved.pop(0), gout), ctx.nu_ref, ctx.geom)
+        return (gu, gnu) + (None,) * 11
+
+
+class FEMResidualFunction(torch.autograd.Function):
+    """loss = sum(R^2); dL/du = mask( K(nu) (2R) ) -- one more pass of the same operator
+    (K is symmetric; R is already zero on the Dirichlet nodes)."""
+
+    @staticmethod
+    def forward(ctx, u, geom, nu, f, dirichlet, jac):
+        loss, R = residual_raw(geom, u.detach(), nu, f, dirichlet, jac, True)
+        ctx.geom, ctx.nu, ctx.dirichlet, ctx.jac, ctx.u_ref = geom, nu, dirichlet, jac, u
+        ctx.save_for_backward(R)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        (R,) = ctx.saved_tensors
+        _, KR = residual_raw(ctx.geom, R, ctx.nu, None, ctx.dirichlet, ctx.jac, False)
+        g = KR.mul_(2.0)
+        g = scale_inplace_(g, gout)
+        return (_like_input(g, ctx.u_ref, ctx.geom),) + (None,) * 5
+
+
+_WHICH = {"N": 0, "dx": 1, "dy": 2, "dz": 3}
+
+
+def _gp_raw(geom: Geometry, t: torch.Tensor, which: int) -> torch.Tensor:
+    tc = _canon(t, geom, "tensor")
+    B = tc.shape[0]
+    g = _geom_struct(geom, B)
+    out = torch.empty((B, geom.ngp_1d ** geom.nsd) + geom.elems, dtype=torch.float32, device=tc.device)
+    fld = _field(tc, B, geom.nsd)
+    stream = torch.cuda.current_stream(tc.device).cuda_stream
+    lib = L.lib()
+    fn = lib.dn_fem_gp_eval_2d_f32 if geom.nsd == 2 else lib.dn_fem_gp_eval_3d_f32
+    with torch.cuda.device(tc.device):
+        rc = fn(C.byref(fld), C.byref(g), which, _ptr(out), C.c_void_p(stream))
+    L.check(rc, "dn_fem_gp_eval")
+    return out
+
+
+class GaussPointEvalFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, geom, which):
+        ctx.geom, ctx.which, ctx.t_ref = geom, which, t
+        return _gp_raw(geom, t.detach(), which)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        geom = ctx.geom
+        gout = gout.contiguous()
+        B = gout.shape[0]
+        g = _geom_struct(geom, B)
+        gin = torch.empty((B,) + geom.spatial, dtype=torch.float32, device=gout.device)
+        stream = torch.cuda.current_stream(gout.device).cuda_stream
+        lib = L.lib()
+        fn = lib.dn_fem_gp_eval_adj_2d_f32 if geom.nsd == 2 else lib.dn_fem_gp_eval_adj_3d_f32
+        with torch.cuda.device(gout.device):
+            rc = fn(_ptr(gout), C.byref(g), ctx.which, _ptr(gin), C.c_void_p(stream))
+        L.check(rc, "dn_fem_gp_eval_adj")
+        return _like_input(gin, ctx.t_ref, geom), None, None
+
+
+# ------------------------------------------------------------------------------ public functional API
+def fem_energy(geom: Geometry, u, nu=None, f=None, f_gp=None, dirichlet: Sequence = (),
+               nu_zero_mask=None, c_k=1.0, c_f=1.0, scale=1.0, reduction="mean", z_own=None,
+               mean_count=0.0) -> torch.Tensor:
+    """Fused Poisson energy loss, differentiable w.r.t. u and (2-D) nu."""
+    return FEMEnergyFunction.apply(u, nu, geom, f, f_gp, tuple(dirichlet), nu_zero_mask, c_k, c_f,
+                                   scale, reduction, z_own, mean_count)
+
+
+def fem_energy_and_grad(geom: Geometry, u, **kw):
+    """(loss, dloss/du) from ONE launch, outside autograd (LBFGS closures, benchmarks)."""
+    loss, grad, _ = energy_raw(geom, u, **kw)
+    return loss, grad
+
+
+def fem_residual(geom: Geometry, u, nu=None, f=None, dirichlet: Sequence = (), jac=1.0) -> torch.Tensor:
+    return FEMResidualFunction.apply(u, geom, nu, f, tuple(dirichlet), jac)
+
+
+def gp_eval(geom: Geometry, t: torch.Tensor, which: str = "N") -> torch.Tensor:
+    return GaussPointEvalFunction.apply(t, geom, _WHICH[which])

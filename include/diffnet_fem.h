@@ -1,0 +1,171 @@
+/*
+ * diffnet_fem.h -- C ABI of libdiffnet_fem.so: the B200 (sm_100a) FEM-loss hot path of DiffNet.
+ *
+ * The reference (adityabalu/DiffNet) has no FFI; its seam is a Python method contract
+ * (SURVEY.md 8b).  Each entry point below names the reference code it replaces:
+ *
+ *   dn_fem_energy_{2d,3d}_f32   the user loss() body built from gauss_pt_evaluation{,_der_x,
+ *                               _der_y,_der_z} (DiffNet/DiffNetFEM.py:7-18,143-156) + torch.where
+ *                               Dirichlet masking + the energy integrand + sum over Gauss points +
+ *                               mean over elements, AND its autograd backward w.r.t. u (and nu):
+ *                               examples/poisson/single_instance/0_base.py:31-56,
+ *                               12_klsum.py:53-78, IBN/poisson-2d/parametric/
+ *                               e1_complex_immersed_background.py:33-58, e2_..._neumann.py:33-60,
+ *                               IBN/poisson-3d/parametric/IBN_3D.py:114-136,
+ *                               IBN/poisson-3d/non-parametric/solve_in_object_3d.py:75-102.
+ *   dn_fem_residual_{2d,3d}_f32 the assembled-residual ("resmin") body: per-element residual,
+ *                               Q1 scatter-add assembly, Dirichlet zeroing, sum(R^2):
+ *                               12_klsum.py:46-51,80-132; tests/test.py:36-79; tests/test3D.py:36-85.
+ *   dn_fem_gp_eval_{2d,3d}_f32  gauss_pt_eval / gauss_pt_evaluation* themselves
+ *   dn_fem_gp_eval_adj_*        (DiffNetFEM.py:7-18,143-156) and their autograd backward
+ *                               (convolution_backward = scatter-transpose).
+ *   dn_scale_inplace_f32        autograd's  grad_input = grad_output * dL/du.
+ *
+ * Conventions
+ *   - All pointers in dn_field / outputs are DEVICE pointers, fp32, x (innermost) contiguous.
+ *     Nodal fields are (B, nz, ny, nx) [nz = 1 in 2-D]; strides are in ELEMENTS and arbitrary
+ *     (channel slices of a (B,3,H,W) tensor are passed as-is: stride_b = 3*H*W); stride_b = 0
+ *     broadcasts one field over the batch.
+ *   - Outputs (grad_u, grad_nu, residual, gp-eval results) are dense/contiguous.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *     allocates nothing and keeps no device state.  The caller owns all buffers.
+ *   - `workspace`: at least dn_fem_workspace_bytes() bytes, 16-byte aligned, and ZERO-FILLED
+ *     BEFORE ITS FIRST USE; a call leaves it zero-filled-equivalent for the next call on the same
+ *     stream (the ticket counter self-resets).  Do not share one workspace between streams.
+ *   - Return value: DN_OK or a negative dn_status; dn_last_error() gives the text (thread-local).
+ *   - No CPU fallback: non-sm_100 devices get DN_EARCH.
+ */
+#ifndef DIFFNET_FEM_H_
+#define DIFFNET_FEM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DN_ABI_VERSION 1
+#define DN_MAX_MASKS 3
+
+typedef enum dn_status {
+  DN_OK = 0,
+  DN_EINVAL = -1,      /* bad shape / stride / null pointer / unsupported option */
+  DN_EARCH = -2,       /* device is not sm_100 (B200) */
+  DN_ECUDA = -3,       /* CUDA launch/runtime error, see dn_last_error() */
+  DN_EWORKSPACE = -4   /* workspace missing or too small */
+} dn_status;
+
+/* One fp32 field on the mesh nodes.  ptr == NULL means "absent". */
+typedef struct dn_field {
+  const float* ptr;
+  int64_t stride_b;    /* batch stride (0 = broadcast) */
+  int64_t stride_z;    /* plane stride (ignored in 2-D) */
+  int64_t stride_y;    /* row stride */
+} dn_field;
+
+/* Dirichlet condition  u = where(mask > 0.5, value [+ value_field], u)   (0_base.py:41-42,
+ * e8_2d_poisson_mms.py:165).  Conditions are applied in array order: where masks overlap the
+ * LAST one wins; dL/du is exactly 0 wherever any mask fired. */
+typedef struct dn_mask {
+  dn_field mask;         /* fp32 0/1 field, strict > 0.5 */
+  dn_field value_field;  /* optional nodal Dirichlet values; ptr NULL -> use `value` */
+  float value;
+  int32_t _pad;
+} dn_mask;
+
+typedef struct dn_geom {
+  int32_t nsd;           /* 2 or 3 */
+  int32_t batch;         /* B */
+  int32_t nx, ny, nz;    /* NODES per direction (domain_sizeX/Y/Z); nz = 1 in 2-D */
+  int32_t ngp_1d;        /* 2, 3 or 4 (DiffNetFEM.py:128-141); Q1 basis only */
+  double hx, hy, hz;     /* element sizes (DiffNetFEM.py:47-51) */
+  /* z-slab decomposition (3-D only); all zero = whole domain is local.
+   * Local planes [0,nz) hold global planes [z_global0, z_global0+nz); the loss sums elements
+   * whose lower plane is in [z_own_lo, z_own_hi) (local indices); gradients are written for all
+   * local planes but are complete only on owned ones. */
+  int32_t z_own_lo, z_own_hi;
+  double mean_count;     /* divisor of reduction=mean; 0 -> B * (local element count) */
+} dn_geom;
+
+typedef struct dn_consts {
+  double c_k;            /* multiplies nu * |grad u|^2       */
+  double c_f;            /* multiplies u * f */
+  double scale;          /* overall factor s (e.g. 0.5*(h/2)^2 in 0_base.py:51-52) */
+  int32_t reduction;     /* 0 = mean over batch x elements, 1 = sum */
+  int32_t _pad;
+} dn_consts;
+
+/* which table a gp-eval call uses (DiffNetFEM.py:143-156) */
+typedef enum dn_gp_which { DN_GP_N = 0, DN_GP_DX = 1, DN_GP_DY = 2, DN_GP_DZ = 3 } dn_gp_which;
+
+int dn_abi_version(void);
+const char* dn_last_error(void);
+/* DN_OK if the current CUDA device is sm_100, DN_EARCH / DN_ECUDA otherwise. */
+int dn_device_check(void);
+
+size_t dn_fem_workspace_bytes(const dn_geom* g);
+
+/*
+ * Fused energy loss + gradient.
+ *   loss = S * sum_{b,e} sum_g w_g ( c_k nu_g |grad u'|_g^2 - c_f u'_g f_g ),  S = scale / count
+ *   u'   = u with the Dirichlet conditions applied;  nu' = where(nu_zero_mask > 0.5, 0, nu)
+ *   grad_u[b,node] = dloss/du  (0 at Dirichlet nodes);  grad_nu likewise (optional).
+ * nu == NULL means nu == 1 (IBN_3D.py:132); f and fgp NULL means no source term; at most one of
+ * f (nodal, (B|1,nz,ny,nx)) and fgp (at Gauss points, dense (B|1, ngp, elems), stride_b given,
+ * other strides ignored; e8_2d_poisson_mms.py:47,154) may be set.
+ * loss_out: device double[1] (nullable); loss_out_f32: device float[1] (nullable).
+ * grad_u NULL -> forward only.
+ */
+int dn_fem_energy_2d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                         const dn_field* fgp, const dn_mask* masks, int nmasks,
+                         const dn_field* nu_zero_mask, const dn_geom* g, const dn_consts* c,
+                         float* grad_u, float* grad_nu, void* workspace, size_t workspace_bytes,
+                         double* loss_out, float* loss_out_f32, void* stream);
+int dn_fem_energy_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                         const dn_field* fgp, const dn_mask* masks, int nmasks,
+                         const dn_field* nu_zero_mask, const dn_geom* g, const dn_consts* c,
+                         float* grad_u, float* grad_nu, void* workspace, size_t workspace_bytes,
+                         double* loss_out, float* loss_out_f32, void* stream);
+
+/*
+ * Assembled residual  R = jac * ( K(nu) u' - F(f) ), zeroed at Dirichlet nodes, and
+ * loss = sum(R^2)  (12_klsum.py:80-132).  `residual` (dense (B,nz,ny,nx)) is required: it is
+ * what the backward pass consumes.  If apply_masks_to_input == 0 the Dirichlet VALUES are not
+ * substituted into u (only the output is zeroed): that is the operator  v -> mask(K(nu) v)
+ * the backward pass needs (dL/du = mask( K(nu) (2R) )).
+ */
+int dn_fem_residual_2d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                           const dn_mask* masks, int nmasks, int apply_masks_to_input,
+                           const dn_geom* g, double jac, float* residual, void* workspace,
+                           size_t workspace_bytes, double* loss_out, float* loss_out_f32,
+                           void* stream);
+int dn_fem_residual_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                           const dn_mask* masks, int nmasks, int apply_masks_to_input,
+                           const dn_geom* g, double jac, float* residual, void* workspace,
+                           size_t workspace_bytes, double* loss_out, float* loss_out_f32,
+                           void* stream);
+
+/*
+ * Gauss-point evaluation  out[b, G, elem] = sum_a T_which[G][a] * in[b, node(elem,a)]
+ * (gauss_pt_eval, DiffNetFEM.py:7-18), G = ngp_1d*jgp + igp (2-D), ngp_1d^2*kgp + ngp_1d*jgp + igp
+ * (3-D); out dense (B, ngp_1d^nsd, [nz-1,] ny-1, nx-1).  The adjoint scatters a cotangent of that
+ * shape back to the nodes: grad_in dense (B, nz, ny, nx) (fully overwritten).
+ */
+int dn_fem_gp_eval_2d_f32(const dn_field* in, const dn_geom* g, int which, float* out,
+                          void* stream);
+int dn_fem_gp_eval_3d_f32(const dn_field* in, const dn_geom* g, int which, float* out,
+                          void* stream);
+int dn_fem_gp_eval_adj_2d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in,
+                              void* stream);
+int dn_fem_gp_eval_adj_3d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in,
+                              void* stream);
+
+/* x[i] *= *factor_dev for i < n, skipping all memory traffic when *factor_dev == 1.0f
+ * (the usual loss.backward() case).  factor_dev is a device pointer: no host sync. */
+int dn_scale_inplace_f32(float* x, size_t n, const float* factor_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFNET_FEM_H_ */

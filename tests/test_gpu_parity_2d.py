@@ -1,0 +1,319 @@
+"""2-D parity: the CUDA path (through the C ABI) vs. the oracle and the golden vectors.
+
+Tolerances (north_star): loss rel <= 1e-5, gradient rel-L2 <= 1e-4, gradient exactly 0 on
+Dirichlet nodes.  The oracle truth is evaluated in fp64 on the CPU.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2, rel_scalar
+from helpers import GRAD_RTOL, LOSS_RTOL, assert_parity, oracle_energy, oracle_residual
+from diffnet_b200 import DiffNet2DFEM
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_inputs(B, H, W, seed=0, smooth=False):
+    g = torch.Generator().manual_seed(seed)
+    if smooth:
+        yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+        u = (torch.sin(np.pi * xx) * torch.sin(np.pi * yy))[None, None].repeat(B, 1, 1, 1)
+        u = u + 0.01 * torch.randn(B, 1, H, W, generator=g)
+    else:
+        u = torch.randn(B, 1, H, W, generator=g)
+    nu = torch.exp(0.5 * torch.randn(B, 1, H, W, generator=g))
+    f = torch.randn(B, 1, H, W, generator=g)
+    bc1 = torch.zeros(B, 1, H, W); bc1[..., 0] = 1
+    bc2 = torch.zeros(B, 1, H, W); bc2[..., -1] = 1
+    inputs = torch.cat([nu, bc1, bc2], 1)
+    return u, inputs, f
+
+
+def run_energy(fem, u, **kw):
+    """CUDA loss + grad via autograd (the user-facing path)."""
+    ud = u.to(DEV).requires_grad_(True)
+    kwd = {}
+    for k, v in kw.items():
+        if torch.is_tensor(v):
+            kwd[k] = v.to(DEV)
+        elif k == "dirichlet":
+            kwd[k] = [(m.to(DEV), (val.to(DEV) if torch.is_tensor(val) else val)) for m, val in v]
+        else:
+            kwd[k] = v
+    loss = fem.energy_loss(ud, **kwd)
+    loss.backward()
+    return loss.detach().cpu(), ud.grad.detach().cpu()
+
+
+SIZES = [(1, 8, 8), (2, 9, 12), (3, 21, 37), (2, 64, 64), (1, 66, 130), (2, 40, 256), (1, 33, 260),
+         (2, 128, 512), (1, 17, 516)]
+
+
+@pytest.mark.parametrize("B,H,W", SIZES)
+def test_energy_e1_sizes(B, H, W):
+    """E1 (12_klsum.py:53-78) over aligned, odd (scalar path) and multi-strip widths."""
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W)
+    u, inputs, f = make_inputs(B, H, W, seed=H * 1000 + W)
+    nu, bc1, bc2 = inputs[:, 0:1], inputs[:, 1:2], inputs[:, 2:3]
+    kw = dict(nu=nu, f=f, dirichlet=[(bc1, 1.0), (bc2, 0.0)])
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, masks=(bc1, bc2), what=f"E1 {B}x{H}x{W}")
+
+
+@pytest.mark.parametrize("variant", ["E2", "E3", "E4", "E5", "E6", "nomask", "onemask", "threemask"])
+def test_energy_family(variant):
+    """The loss family of SURVEY.md App. A.4 on one 48 x 72 mesh."""
+    B, H, W = 3, 48, 72
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_lengths=(1.5, 1.0, 1.0), domain_size=W)
+    u, inputs, f = make_inputs(B, H, W, seed=7)
+    nu, bc1, bc2 = inputs[:, 0:1], inputs[:, 1:2], inputs[:, 2:3]
+    obj = torch.zeros_like(nu); obj[:, :, 10:20, 30:50] = 1
+    kw = {
+        "E2": dict(nu=nu, f=f, dirichlet=[(bc1, 1.0), (bc2, 0.0)], scale=0.5 * (0.5 * fem.h) ** 2),
+        "E3": dict(nu=nu, f=f, dirichlet=[(bc1, 1.0), (bc2, 0.0)], c_k=0.5),
+        "E4": dict(f=f, dirichlet=[(bc1, 1.0), (bc2, 0.0)]),
+        "E5": dict(nu=nu, f=f, nu_zero_mask=obj, dirichlet=[(bc1, 1.0), (bc2, 0.0)]),
+        "E6": dict(nu=nu, dirichlet=[(bc1, 1.0), (bc2, 0.0)], c_k=0.5, c_f=0.0),
+        "nomask": dict(nu=nu, f=f),
+        "onemask": dict(nu=nu, f=f, dirichlet=[(obj, 0.25)], reduction="sum"),
+        "threemask": dict(nu=nu, f=f, dirichlet=[(obj, 0.5), (bc1, 1.0), (bc2, 0.0)]),
+    }[variant]
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    masks = [m for m, _ in kw.get("dirichlet", [])]
+    assert_parity(loss, grad, lref, gref, masks=masks, what=variant)
+
+
+def test_mask_precedence_and_overlap():
+    """Later Dirichlet entries win where masks overlap (0_base.py:41-42); IBN_3D-style
+    'source wins over sink' is the reversed order."""
+    B, H, W = 2, 24, 32
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W)
+    u, inputs, f = make_inputs(B, H, W, seed=3)
+    a = torch.zeros(B, 1, H, W); a[:, :, 4:12, 4:20] = 1
+    b = torch.zeros(B, 1, H, W); b[:, :, 8:16, 10:28] = 1
+    for order in ([(a, 1.0), (b, 0.0)], [(b, 0.0), (a, 1.0)]):
+        kw = dict(nu=inputs[:, 0:1], f=f, dirichlet=order)
+        loss, grad = run_energy(fem, u, **kw)
+        lref, gref = oracle_energy(fem, u, **kw)
+        assert_parity(loss, grad, lref, gref, masks=(a, b), what="overlap")
+
+
+def test_dirichlet_value_field_and_f_at_gauss_points():
+    """E3 with u = where(bc, u_bc, u) and analytic forcing at the Gauss points
+    (e8_2d_poisson_mms.py:47,154,165,175)."""
+    B, H, W = 2, 30, 44
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W)
+    u, inputs, _ = make_inputs(B, H, W, seed=11)
+    nu = inputs[:, 0:1]
+    edge = torch.zeros(1, 1, H, W); edge[..., 0] = 1; edge[..., -1] = 1; edge[:, :, 0] = 1; edge[:, :, -1] = 1
+    u_bc = torch.randn(1, 1, H, W)
+    xg, yg = fem.xgp, fem.ygp
+    f_gp = (2 * np.pi ** 2 * torch.sin(np.pi * xg) * torch.sin(np.pi * yg)).float()
+    kw = dict(nu=nu, f_gp=f_gp, dirichlet=[(edge, u_bc)], c_k=0.5)
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, masks=(edge.expand(B, 1, H, W),), what="vf+fgp")
+
+
+@pytest.mark.parametrize("ngp", [3, 4])
+def test_more_gauss_points(ngp):
+    """ngp_1d = 3, 4: the closed form uses the second moment of the reference's own rule."""
+    B, H, W = 2, 20, 28
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W, ngp_1d=ngp)
+    u, inputs, f = make_inputs(B, H, W, seed=ngp)
+    kw = dict(nu=inputs[:, 0:1], f=f, dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)])
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, what=f"ngp{ngp}")
+    f_gp = torch.randn(1, ngp * ngp, H - 1, W - 1)
+    kw = dict(nu=inputs[:, 0:1], f_gp=f_gp, c_k=0.5)
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, what=f"ngp{ngp} fgp")
+
+
+def test_strided_channel_slices_and_broadcast():
+    """nu/bc1/bc2 as channel slices of one (B,3,H,W) tensor (no .contiguous()), f broadcast
+    over the batch, u a bare (H,W) parameter."""
+    B, H, W = 4, 32, 64
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W)
+    u, inputs, f = make_inputs(B, H, W, seed=5)
+    inp = inputs.to(DEV)
+    f1 = f[:1]
+    ud = u.to(DEV).requires_grad_(True)
+    loss = fem.energy_loss(ud, nu=inp[:, 0:1], f=f1.to(DEV),
+                           dirichlet=[(inp[:, 1:2], 1.0), (inp[:, 2:3], 0.0)])
+    loss.backward()
+    lref, gref = oracle_energy(fem, u, nu=inputs[:, 0:1], f=f1,
+                               dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)])
+    assert_parity(loss.cpu(), ud.grad.cpu(), lref, gref, what="strided")
+    # bare (H, W) parameter against batched inputs: gradient is summed over the batch
+    ub = u[0, 0].clone()
+    ubd = ub.to(DEV).requires_grad_(True)
+    loss = fem.energy_loss(ubd, nu=inp[:, 0:1], f=f1.to(DEV), dirichlet=[(inp[:, 1:2], 1.0)])
+    loss.backward()
+    lref, gref = oracle_energy(fem, ub, nu=inputs[:, 0:1], f=f1, dirichlet=[(inputs[:, 1:2], 1.0)])
+    assert tuple(ubd.grad.shape) == (H, W)
+    assert_parity(loss.cpu(), ubd.grad.cpu(), lref, gref, what="bare u")
+
+
+def test_grad_output_scaling_and_grad_nu():
+    """backward multiplies by grad_output; d loss / d nu (16_topopt.py:124,153)."""
+    B, H, W = 2, 28, 36
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W)
+    u, inputs, f = make_inputs(B, H, W, seed=9)
+    nu, bc1, bc2 = inputs[:, 0:1], inputs[:, 1:2], inputs[:, 2:3]
+    ud = u.to(DEV).requires_grad_(True)
+    nud = nu.to(DEV).clone().requires_grad_(True)
+    loss = 3.5 * fem.energy_loss(ud, nu=nud, f=f.to(DEV), dirichlet=[(bc1.to(DEV), 1.0), (bc2.to(DEV), 0.0)])
+    loss.backward()
+    from helpers import oracle_for, to64
+    from oracle import losses as OL
+    o = oracle_for(fem)
+    u64, nu64 = to64(u).requires_grad_(True), to64(nu).requires_grad_(True)
+    lref = 3.5 * OL.energy_loss(o, u64, nu=nu64, f=to64(f), dirichlet=[(to64(bc1), 1.0), (to64(bc2), 0.0)])
+    gu, gn = torch.autograd.grad(lref, (u64, nu64))
+    assert rel_scalar(loss.cpu(), lref) <= LOSS_RTOL
+    assert rel_l2(ud.grad.cpu(), gu) <= GRAD_RTOL
+    assert rel_l2(nud.grad.cpu(), gn) <= GRAD_RTOL
+
+
+def test_golden_vectors(golden):
+    """Outputs of the real reference (tests/golden/make_golden.py)."""
+    g = golden("ref_2d_rect")
+    X, Y = (int(v) for v in g["sizes"])
+    fem = DiffNet2DFEM(None, domain_sizes=(X, Y, 1), domain_lengths=(1.5, 1.0, 1.0), domain_size=X,
+                       domain_length=1.5)
+    u, inputs, f = g.t("u"), g.t("inputs"), g.t("forcing")
+    nu, bc1, bc2 = inputs[:, 0:1], inputs[:, 1:2], inputs[:, 2:3]
+    d = [(bc1, 1.0), (bc2, 0.0)]
+    for key, kw in (("E1", dict(nu=nu, f=f, dirichlet=d)),
+                    ("E2", dict(nu=nu, f=f, dirichlet=d, scale=0.5 * (0.5 * fem.h) ** 2)),
+                    ("E3fgp", dict(nu=nu, f_gp=g.t("f_gp"), dirichlet=[(bc2, g.t("u_bc"))], c_k=0.5))):
+        loss, grad = run_energy(fem, u, **kw)
+        assert rel_scalar(loss, g[key + ".loss64"]) <= LOSS_RTOL, key
+        assert rel_l2(grad, g[key + ".grad64"]) <= GRAD_RTOL, key
+        assert rel_scalar(loss, g[key + ".loss"]) <= LOSS_RTOL, key
+    g = golden("ref_2d_neumann")
+    fem = DiffNet2DFEM(None, domain_size=17)
+    u, inputs, f = g.t("u"), g.t("inputs"), g.t("forcing")
+    nu, obj, bc2, bc3 = (inputs[:, i:i + 1] for i in range(4))
+    loss, grad = run_energy(fem, u, nu=nu, f=f, nu_zero_mask=obj, dirichlet=[(bc2, 1.0), (bc3, 0.0)])
+    assert rel_scalar(loss, g["E5.loss64"]) <= LOSS_RTOL and rel_l2(grad, g["E5.grad64"]) <= GRAD_RTOL
+    g = golden("ref_2d_ngp")
+    u, inputs, f = g.t("u"), g.t("inputs"), g.t("forcing")
+    for ngp in (3, 4):
+        fem = DiffNet2DFEM(None, domain_size=10, ngp_1d=ngp)
+        loss, grad = run_energy(fem, u, nu=inputs[:, 0:1], f=f,
+                                dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)])
+        assert rel_scalar(loss, g[f"E1_ngp{ngp}.loss64"]) <= LOSS_RTOL
+        assert rel_l2(grad, g[f"E1_ngp{ngp}.grad64"]) <= GRAD_RTOL
+
+
+def test_residual_form(golden):
+    """Assembled residual sum(R^2) and its gradient (12_klsum.py:80-132, tests/test.py)."""
+    B, H, W = 2, 26, 40
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W)
+    u, inputs, f = make_inputs(B, H, W, seed=13, smooth=True)
+    nu, bc1, bc2 = inputs[:, 0:1], inputs[:, 1:2], inputs[:, 2:3]
+    d = [(bc1, 1.0), (bc2, 0.0)]
+    ud = u.to(DEV).requires_grad_(True)
+    loss = fem.residual_loss(ud, nu=nu.to(DEV), f=f.to(DEV), dirichlet=[(m.to(DEV), v) for m, v in d],
+                             jac=1.0)
+    loss.backward()
+    lref, gref = oracle_residual(fem, u, nu=nu, f=f, dirichlet=d, jac=1.0)
+    assert_parity(loss.cpu(), ud.grad.cpu(), lref, gref, masks=(bc1, bc2), what="resmin")
+    g = golden("ref_2d_rect")
+    X, Y = (int(v) for v in g["sizes"])
+    fem = DiffNet2DFEM(None, domain_sizes=(X, Y, 1), domain_lengths=(1.5, 1.0, 1.0), domain_size=X,
+                       domain_length=1.5)
+    u, inputs, f = g.t("u"), g.t("inputs"), g.t("forcing")
+    ud = u.to(DEV).requires_grad_(True)
+    inp = inputs.to(DEV)
+    loss = fem.residual_loss(ud, nu=inp[:, 0:1], f=f.to(DEV), dirichlet=[(inp[:, 1:2], 1.0), (inp[:, 2:3], 0.0)])
+    loss.backward()
+    assert rel_scalar(loss.cpu(), g["resmin.loss64"]) <= LOSS_RTOL
+    assert rel_l2(ud.grad.cpu(), g["resmin.grad64"]) <= GRAD_RTOL
+
+
+def test_gauss_point_evaluation_and_adjoint(golden):
+    """gauss_pt_evaluation{,_der_x,_der_y} + their backward vs the reference's conv outputs."""
+    g = golden("ref_2d_rect")
+    X, Y = (int(v) for v in g["sizes"])
+    fem = DiffNet2DFEM(None, domain_sizes=(X, Y, 1), domain_lengths=(1.5, 1.0, 1.0), domain_size=X,
+                       domain_length=1.5)
+    u = g.t("u").to(DEV)
+    for key, fn in (("N", fem.gauss_pt_evaluation), ("dx", fem.gauss_pt_evaluation_der_x),
+                    ("dy", fem.gauss_pt_evaluation_der_y)):
+        out = fn(u)
+        assert out.shape == g["gp." + key].shape
+        assert rel_l2(out.cpu(), g["gp." + key]) <= 1e-6, key
+    # a user-written (un-fused) loss body on the CUDA gp-eval ops == oracle autograd
+    B, H, W = 2, 19, 23
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W, ngp_1d=3)
+    u, inputs, f = make_inputs(B, H, W, seed=21)
+    ud = u.to(DEV).requires_grad_(True)
+    nu_gp = fem.gauss_pt_evaluation(inputs[:, 0:1].to(DEV))
+    ux, uy, ug = fem.gauss_pt_evaluation_der_x(ud), fem.gauss_pt_evaluation_der_y(ud), fem.gauss_pt_evaluation(ud)
+    w = fem.gpw.to(DEV)[None, :, None, None]
+    loss = torch.mean(torch.sum(w * (nu_gp * (ux ** 2 + uy ** 2) - ug * fem.gauss_pt_evaluation(f.to(DEV))), 1))
+    loss.backward()
+    lref, gref = oracle_energy(fem, u, nu=inputs[:, 0:1], f=f)
+    assert_parity(loss.cpu(), ud.grad.cpu(), lref, gref, what="unfused body")
+
+
+def test_full_size_properties():
+    """BASELINE sizes (256^2 B=64, 512^2 B=16): size-independent properties instead of the
+    oracle -- Euler identity <grad,u> = 2E for the pure stiffness energy, exact zero energy and
+    gradient for constant u, quadratic scaling, chunking independence, and run-to-run bit
+    reproducibility."""
+    for B, N in ((64, 256), (16, 512)):
+        fem = DiffNet2DFEM(None, domain_size=N, batch_size=B)
+        g = torch.Generator(device=DEV).manual_seed(N)
+        u = torch.randn(B, 1, N, N, device=DEV, generator=g)
+        nu = torch.exp(0.3 * torch.randn(B, 1, N, N, device=DEV, generator=g))
+        loss, grad = fem.energy_loss_and_grad(u, nu=nu)
+        euler = float((grad.double() * u[:, 0].double()).sum())
+        assert rel_scalar(euler, 2.0 * float(loss)) < 2e-5
+        l2, g2 = fem.energy_loss_and_grad(2.0 * u, nu=nu)
+        assert rel_scalar(l2, 4.0 * float(loss)) < 1e-5 and rel_l2(g2, 2.0 * grad) < 1e-5
+        lc, gc = fem.energy_loss_and_grad(torch.full_like(u, 3.0), nu=nu)
+        assert float(lc) == 0.0 and float(gc.abs().max()) == 0.0
+        la, ga = fem.energy_loss_and_grad(u, nu=nu)
+        assert torch.equal(la, loss) and torch.equal(ga, grad)            # deterministic
+        old = os.environ.get("DN_R_2D")
+        try:
+            os.environ["DN_R_2D"] = "37"                                   # different row chunking
+            lb, gb = fem.energy_loss_and_grad(u, nu=nu)
+        finally:
+            if old is None:
+                os.environ.pop("DN_R_2D")
+            else:
+                os.environ["DN_R_2D"] = old
+        assert rel_scalar(lb, loss) < 1e-6 and torch.equal(gb, grad)       # seams are exact
+        # batch samples are independent: sample 3 alone gives its slice of the gradient
+        l1, g1 = fem.energy_loss_and_grad(u[3:4], nu=nu[3:4], reduction="sum")
+        ls, gs = fem.energy_loss_and_grad(u, nu=nu, reduction="sum")
+        assert torch.equal(g1[0], gs[3])
+
+
+def test_errors_are_loud():
+    from diffnet_b200._lib import DiffNetFEMError
+    fem = DiffNet2DFEM(None, domain_size=16)
+    u = torch.zeros(1, 1, 16, 16, device=DEV)
+    with pytest.raises(DiffNetFEMError):
+        fem.energy_loss(torch.zeros(1, 1, 15, 16, device=DEV))
+    with pytest.raises(DiffNetFEMError):
+        fem.energy_loss(u.double())
+    with pytest.raises(DiffNetFEMError):
+        fem.energy_loss(u, f=u, f_gp=torch.zeros(1, 4, 15, 15, device=DEV))
+    with pytest.raises(DiffNetFEMError):
+        fem.energy_loss(u, dirichlet=[(u, 0.0)] * 4)
+    with pytest.raises(DiffNetFEMError):
+        fem.energy_loss(u.cpu())

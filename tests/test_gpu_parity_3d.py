@@ -1,0 +1,190 @@
+"""3-D parity: the CUDA path (through the C ABI) vs. the oracle and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2, rel_scalar
+from helpers import GRAD_RTOL, LOSS_RTOL, assert_parity, oracle_energy, oracle_residual
+from diffnet_b200 import DiffNet3DFEM
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_inputs(B, D, H, W, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    u = torch.randn(B, 1, D, H, W, generator=g)
+    nu = torch.exp(0.5 * torch.randn(B, 1, D, H, W, generator=g))
+    f = torch.randn(B, 1, D, H, W, generator=g)
+    src = (torch.rand(B, 1, D, H, W, generator=g) > 0.93).float()
+    sink = torch.zeros(B, 1, D, H, W)
+    sink[:, :, 0] = 1; sink[:, :, -1] = 1; sink[:, :, :, 0] = 1
+    sink[:, :, :, -1] = 1; sink[..., 0] = 1; sink[..., -1] = 1
+    return u, nu, f, src, sink
+
+
+def dev(x):
+    if torch.is_tensor(x):
+        return x.to(DEV)
+    if isinstance(x, (list, tuple)):
+        return type(x)(dev(v) for v in x)
+    return x
+
+
+def run_energy(fem, u, **kw):
+    ud = u.to(DEV).requires_grad_(True)
+    loss = fem.energy_loss(ud, **{k: dev(v) for k, v in kw.items()})
+    loss.backward()
+    return loss.detach().cpu(), ud.grad.detach().cpu()
+
+
+SIZES = [(1, 5, 6, 8), (2, 5, 6, 7), (1, 9, 11, 13), (2, 12, 20, 16), (1, 20, 33, 64), (1, 10, 12, 128),
+         (1, 7, 9, 132), (1, 6, 10, 260), (1, 5, 8, 520), (2, 16, 16, 16)]
+
+
+@pytest.mark.parametrize("B,D,H,W", SIZES)
+def test_energy_sizes(B, D, H, W):
+    """Full Poisson (u, nu, f, two masks) over aligned / odd / multi-tile meshes."""
+    fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_lengths=(1.0, 0.8, 0.5), domain_size=W)
+    u, nu, f, src, sink = make_inputs(B, D, H, W, seed=D * 10000 + H * 100 + W)
+    kw = dict(nu=nu, f=f, dirichlet=[(sink, 0.0), (src, 1.0)])
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, masks=(src, sink), what=f"3D {B}x{D}x{H}x{W}")
+
+
+@pytest.mark.parametrize("variant", ["ibn3d", "inobj", "nomask", "numask", "E6", "sum"])
+def test_energy_family(variant):
+    B, D, H, W = 2, 14, 18, 24
+    fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_size=W)
+    u, nu, f, src, sink = make_inputs(B, D, H, W, seed=17)
+    kw = {
+        "ibn3d": dict(f=f, dirichlet=[(sink, 0.0), (src, 1.0)]),                 # IBN_3D.py:114-136
+        "inobj": dict(nu=nu, f=f, dirichlet=[(src, 0.0)], c_k=0.5),              # solve_in_object_3d.py:75-102
+        "nomask": dict(nu=nu, f=f),
+        "numask": dict(nu=nu, f=f, nu_zero_mask=src, dirichlet=[(sink, 0.0)]),
+        "E6": dict(nu=nu, dirichlet=[(sink, 0.0), (src, 1.0)], c_k=0.5, c_f=0.0),  # 9_voxel_3d.py:119
+        "sum": dict(nu=nu, f=f, dirichlet=[(sink, 0.0)], reduction="sum", scale=0.125),
+    }[variant]
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, masks=[m for m, _ in kw.get("dirichlet", [])], what=variant)
+
+
+@pytest.mark.parametrize("ngp", [2, 3])
+def test_f_at_gauss_points_and_value_field(ngp):
+    """e8_3d_poisson_mms.py:48,143,165: forcing at Gauss points + nodal Dirichlet field."""
+    B, D, H, W = 1, 8, 10, 12
+    fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_size=W, ngp_1d=ngp)
+    u, nu, f, src, sink = make_inputs(B, D, H, W, seed=23)
+    u_bc = torch.randn(1, 1, D, H, W)
+    f_gp = torch.randn(1, ngp ** 3, D - 1, H - 1, W - 1)
+    kw = dict(nu=nu, f_gp=f_gp, dirichlet=[(sink, u_bc)], c_k=0.5)
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, masks=(sink,), what=f"fgp ngp{ngp}")
+
+
+def test_golden_vectors(golden):
+    g = golden("ref_3d_box")
+    X, Y, Z = (int(v) for v in g["sizes"])
+    fem = DiffNet3DFEM(None, domain_sizes=(X, Y, Z), domain_lengths=(1.0, 0.8, 0.5), domain_size=X)
+    u, inputs, f = g.t("u"), g.t("inputs"), g.t("forcing")
+    src, sink = g.t("source"), g.t("sink")
+    loss, grad = run_energy(fem, u, f=f, dirichlet=[(sink, 0.0), (src, 1.0)])
+    assert rel_scalar(loss, g["ibn3d.loss64"]) <= LOSS_RTOL and rel_l2(grad, g["ibn3d.grad64"]) <= GRAD_RTOL
+    loss, grad = run_energy(fem, u, nu=inputs[:, 0:1], f=f, dirichlet=[(inputs[:, 1:2], 0.0)], c_k=0.5)
+    assert rel_scalar(loss, g["inobj.loss64"]) <= LOSS_RTOL and rel_l2(grad, g["inobj.grad64"]) <= GRAD_RTOL
+    # bare (D,H,W) parameter, B = 1 (solve_in_object_3d.py:198-199)
+    ub = u[0, 0].to(DEV).requires_grad_(True)
+    inp = inputs[:1].to(DEV)
+    loss = fem.energy_loss(ub, nu=inp[:, 0:1], f=f[:1].to(DEV), dirichlet=[(inp[:, 1:2], 0.0)], c_k=0.5)
+    loss.backward()
+    assert tuple(ub.grad.shape) == (Z, Y, X)
+    assert rel_scalar(loss.cpu(), g["inobj_bare.loss64"]) <= LOSS_RTOL
+    assert rel_l2(ub.grad.cpu(), g["inobj_bare.grad64"]) <= GRAD_RTOL
+    for key, fn in (("N", fem.gauss_pt_evaluation), ("dx", fem.gauss_pt_evaluation_der_x),
+                    ("dy", fem.gauss_pt_evaluation_der_y), ("dz", fem.gauss_pt_evaluation_der_z)):
+        out = fn(u.to(DEV))
+        assert out.shape == g["gp." + key].shape
+        assert rel_l2(out.cpu(), g["gp." + key]) <= 1e-6, key
+
+
+def test_residual_form():
+    B, D, H, W = 1, 9, 10, 12
+    fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_size=W)
+    u, nu, f, src, sink = make_inputs(B, D, H, W, seed=29)
+    d = [(sink, 0.0), (src, 1.0)]
+    ud = u.to(DEV).requires_grad_(True)
+    loss = fem.residual_loss(ud, nu=nu.to(DEV), f=f.to(DEV), dirichlet=dev(d), jac=(0.5 * fem.h) ** 3)
+    loss.backward()
+    lref, gref = oracle_residual(fem, u, nu=nu, f=f, dirichlet=d, jac=(0.5 * fem.h) ** 3)
+    assert_parity(loss.cpu(), ud.grad.cpu(), lref, gref, masks=(src, sink), what="resmin3d")
+
+
+def test_unfused_body_on_gp_eval_ops():
+    B, D, H, W = 1, 7, 8, 9
+    fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_size=W)
+    u, nu, f, _, _ = make_inputs(B, D, H, W, seed=31)
+    ud = u.to(DEV).requires_grad_(True)
+    gsq = (fem.gauss_pt_evaluation_der_x(ud) ** 2 + fem.gauss_pt_evaluation_der_y(ud) ** 2
+           + fem.gauss_pt_evaluation_der_z(ud) ** 2)
+    res = fem.gauss_pt_evaluation(nu.to(DEV)) * gsq - fem.gauss_pt_evaluation(ud) * fem.gauss_pt_evaluation(f.to(DEV))
+    loss = torch.mean(torch.sum(res, 1))
+    loss.backward()
+    lref, gref = oracle_energy(fem, u, nu=nu, f=f)
+    assert_parity(loss.cpu(), ud.grad.cpu(), lref, gref, what="unfused 3d")
+
+
+def test_full_size_properties():
+    """64^3 B=16 and 128^3 B=1 (BASELINE sizes): Euler identity, constants, scaling, determinism,
+    independence of the z-chunking / tile shape."""
+    for B, N in ((16, 64), (1, 128)):
+        fem = DiffNet3DFEM(None, domain_size=N)
+        g = torch.Generator(device=DEV).manual_seed(N)
+        u = torch.randn(B, 1, N, N, N, device=DEV, generator=g)
+        nu = torch.exp(0.3 * torch.randn(B, 1, N, N, N, device=DEV, generator=g))
+        loss, grad = fem.energy_loss_and_grad(u, nu=nu)
+        euler = float((grad.double() * u[:, 0].double()).sum())
+        assert rel_scalar(euler, 2.0 * float(loss)) < 2e-5
+        l2, g2 = fem.energy_loss_and_grad(2.0 * u, nu=nu)
+        assert rel_scalar(l2, 4.0 * float(loss)) < 1e-5 and rel_l2(g2, 2.0 * grad) < 1e-5
+        lc, gc = fem.energy_loss_and_grad(torch.full_like(u, 3.0), nu=nu)
+        assert float(lc) == 0.0 and float(gc.abs().max()) == 0.0
+        la, ga = fem.energy_loss_and_grad(u, nu=nu)
+        assert torch.equal(la, loss) and torch.equal(ga, grad)
+        for var, val in (("DN_ZC_3D", "11"), ("DN_ROWS_3D", "6")):
+            os.environ[var] = val
+            try:
+                lb, gb = fem.energy_loss_and_grad(u, nu=nu)
+            finally:
+                os.environ.pop(var)
+            assert rel_scalar(lb, loss) < 1e-6 and rel_l2(gb, grad) < 1e-6, var
+
+
+def test_z_slab_ownership_matches_whole_domain():
+    """slabs with one-plane halos, loss summed over owned layers, gradient complete
+    on owned planes, divided by the GLOBAL element count -- emulated on one GPU."""
+    from diffnet_b200 import ops
+    B, N = 1, 24
+    fem = DiffNet3DFEM(None, domain_size=N)
+    u, nu, f, src, sink = make_inputs(B, N, N, N, seed=37)
+    u, nu, f, src = (t.to(DEV) for t in (u, nu, f, src))
+    d = [(src, 0.0)]
+    loss, grad = fem.energy_loss_and_grad(u, nu=nu, f=f, dirichlet=d, c_k=0.5)
+    total, parts = 0.0, []
+    nslab = 3
+    count = float(B * (N - 1) ** 3)
+    for s in range(nslab):
+        z0, z1 = s * N // nslab, (s + 1) * N // nslab
+        lo, hi = max(z0 - 1, 0), min(z1 + 1, N)
+        geom = ops.Geometry(3, N, N, hi - lo, fem.hx, fem.hy, fem.hz, 2)
+        sl = lambda t: t[:, :, lo:hi]
+        l, g, _ = ops.energy_raw(geom, sl(u), nu=sl(nu), f=sl(f), dirichlet=[(sl(src), 0.0)], c_k=0.5,
+                                 z_own=(z0 - lo, z1 - lo), mean_count=count)
+        total += float(l)
+        parts.append(g[:, z0 - lo:z1 - lo])
+    assert rel_scalar(total, float(loss)) < 1e-5
+    assert rel_l2(torch.cat(parts, 1), grad) < 1e-6
