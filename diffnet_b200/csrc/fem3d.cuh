@@ -246,7 +246,10 @@ __global__ void __launch_bounds__(DN_MAXT_3D) k_fem3d(const P3D p) {
   const bool rhalo = act && (lx == LX - 1) && (x0 + V < p.nx);
   const bool crow = (r < TY) && act && (y + 1 < p.ny);          // this thread computes elements
   const bool own_x = (lx >= 1) || (itx == 0);
-  const bool own_y = (r <= TY - 1) && ((r >= 1) || (ity == 0));
+  // rows 1..TY-1 (plus row 0 of the first tile); the domain's last node row has no element row
+  // below it, so when it lands on the loader row of the LAST tile that tile owns it too
+  const bool own_y = ((r <= TY - 1) && ((r >= 1) || (ity == 0))) ||
+                     ((r == TY) && (y == p.ny - 1) && (ity == p.nty - 1));
   const bool own = act && own_x && own_y;
   const bool lastvalid = (x0 + V) < p.nx;
 

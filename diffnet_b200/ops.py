@@ -10,6 +10,7 @@ CPU path (CPU tensors raise).  See include/diffnet_fem.h for the C side.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -93,6 +94,14 @@ def _geom_struct(geom: Geometry, B: int, z_own=None, mean_count=0.0) -> L.dn_geo
                      float(mean_count))
 
 
+def _new_out(shape, device, dtype=torch.float32) -> torch.Tensor:
+    """Output buffer.  With DN_POISON_OUTPUTS=1 (set by the test-suite) it is NaN-filled first so
+    that a node the kernel failed to write can never pass a parity check by accident."""
+    if os.environ.get("DN_POISON_OUTPUTS"):
+        return torch.full(shape, float("nan"), dtype=dtype, device=device)
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
 _workspaces = {}
 
 
@@ -166,9 +175,9 @@ def energy_raw(geom: Geometry, u, nu=None, f=None, f_gp=None, dirichlet=(), nu_z
     cs = L.dn_consts(float(c_k), float(c_f), float(scale), 0 if reduction == "mean" else 1, 0)
     if reduction not in ("mean", "sum"):
         raise L.DiffNetFEMError("reduction must be 'mean' or 'sum'")
-    grad = torch.empty((B,) + geom.spatial, dtype=torch.float32, device=dev) if want_grad else None
-    grad_nu = torch.empty((B,) + geom.spatial, dtype=torch.float32, device=dev) if want_grad_nu else None
-    loss = torch.empty((), dtype=torch.float32, device=dev)
+    grad = _new_out((B,) + geom.spatial, dev) if want_grad else None
+    grad_nu = _new_out((B,) + geom.spatial, dev) if want_grad_nu else None
+    loss = _new_out((), dev)
     loss64 = torch.empty((), dtype=torch.float64, device=dev) if want_double else None
     lib = L.lib()
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -200,8 +209,8 @@ def residual_raw(geom: Geometry, u, nu=None, f=None, dirichlet=(), jac=1.0, appl
     marr, nm = _masks_struct(dirichlet, geom, B, keep)
     dev = uc.device
     g = _geom_struct(geom, B)
-    R = torch.empty((B,) + geom.spatial, dtype=torch.float32, device=dev)
-    loss = torch.empty((), dtype=torch.float32, device=dev)
+    R = _new_out((B,) + geom.spatial, dev)
+    loss = _new_out((), dev)
     lib = L.lib()
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
@@ -304,7 +313,7 @@ def _gp_raw(geom: Geometry, t: torch.Tensor, which: int) -> torch.Tensor:
     tc = _canon(t, geom, "tensor")
     B = tc.shape[0]
     g = _geom_struct(geom, B)
-    out = torch.empty((B, geom.ngp_1d ** geom.nsd) + geom.elems, dtype=torch.float32, device=tc.device)
+    out = _new_out((B, geom.ngp_1d ** geom.nsd) + geom.elems, tc.device)
     fld = _field(tc, B, geom.nsd)
     stream = torch.cuda.current_stream(tc.device).cuda_stream
     lib = L.lib()
@@ -328,7 +337,7 @@ class GaussPointEvalFunction(torch.autograd.Function):
         gout = gout.contiguous()
         B = gout.shape[0]
         g = _geom_struct(geom, B)
-        gin = torch.empty((B,) + geom.spatial, dtype=torch.float32, device=gout.device)
+        gin = _new_out((B,) + geom.spatial, gout.device)
         stream = torch.cuda.current_stream(gout.device).cuda_stream
         lib = L.lib()
         fn = lib.dn_fem_gp_eval_adj_2d_f32 if geom.nsd == 2 else lib.dn_fem_gp_eval_adj_3d_f32

@@ -16,6 +16,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# every output buffer is NaN-filled before a launch: unwritten nodes cannot pass by accident
+os.environ.setdefault("DN_POISON_OUTPUTS", "1")
 
 
 def pytest_configure(config):
