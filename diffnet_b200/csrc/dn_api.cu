@@ -7,6 +7,7 @@
 
 #include "dn_common.cuh"
 #include "fem2d.cuh"
+#include "fem2d_tma.cuh"
 #include "fem3d.cuh"
 #include "gp_eval.cuh"
 
@@ -180,9 +181,105 @@ static Plan2D plan2d(const dn_geom* g, bool vec4, int sms) {
 
 static size_t ws_bytes_for_grid(long long grid) { return 64 + 8 * (size_t)grid; }
 
+// ---- streaming (bulk-async) 2-D path -------------------------------------------------------
+struct Plan2T { int ok, threads, S, R, nchunks, nf; long long grid; size_t smem; };
+
+static size_t smem_2t(int S, int nf, int nx, int threads) {
+  return (size_t)S * nf * nx * 4 + 16 + (size_t)S * 8 + 2 * (size_t)(threads / 32) * 4;
+}
+
+// Eligibility + launch shape.  `occ` (resident CTAs per SM) may be null: then only the upper
+// bound of the grid matters (workspace sizing).
+static Plan2T plan2t(const dn_geom* g, int nf, int sms, occ2t_fn occ) {
+  Plan2T pl;
+  memset(&pl, 0, sizeof(pl));
+  if (g->nx % 4 != 0 || g->nx < 8) return pl;
+  const int lanes = g->nx / 4;
+  pl.threads = (lanes + 31) / 32 * 32;
+  if (pl.threads > DN_T2_MAXT) return pl;
+  pl.nf = nf;
+  int S = env_int("DN_T2_STAGES", 4);
+  if (S < 2) S = 2;
+  if (S > 16) S = 16;
+  while (S > 2 && smem_2t(S, nf, g->nx, pl.threads) > (size_t)64 * 1024) --S;   // keep >= 3 CTAs/SM
+  pl.S = S;
+  pl.smem = smem_2t(S, nf, g->nx, pl.threads);
+  if (pl.smem > (size_t)kMaxDynSmem) return pl;
+  int cps = occ ? occ(pl.threads, pl.smem) : 8;
+  if (cps < 1) return pl;
+  const int cap = env_int("DN_T2_CPS", 0);
+  if (cap > 0 && cps > cap) cps = cap;
+  // one wave: B * nchunks <= resident slots, chunks of >= Rmin rows (halo rows are re-read
+  // from L2 and their element row recomputed: (R+2)/R reads, (R+1)/R arithmetic)
+  const long long slots = (long long)sms * cps;
+  long long nch = slots / g->batch;
+  if (nch < 1) nch = 1;
+  int R = (int)((g->ny + nch - 1) / nch);
+  int Rmin = env_int("DN_T2_RMIN", 8);
+  if (Rmin < 4) Rmin = 4;
+  if (R < Rmin) R = Rmin;
+  R = env_int("DN_T2_R", R);
+  if (R < 4) R = 4;
+  if (R > g->ny) R = g->ny;
+  pl.R = R;
+  pl.nchunks = (g->ny + R - 1) / R;
+  pl.grid = (long long)g->batch * pl.nchunks;
+  pl.ok = 1;
+  return pl;
+}
+
+static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, void* workspace,
+                 size_t wsb, double* loss_out, float* loss_f32, void* stream, int sms, bool* handled) {
+  *handled = false;
+  const char* path = getenv("DN_2D_PATH");
+  if (path && !strcmp(path, "warp")) return DN_OK;
+  if (!c.vec4 || c.fgp.p || ((uintptr_t)grad % 16 != 0)) return DN_OK;
+  const int NU = c.nu.p ? 1 : 0, F = c.f.p ? 1 : 0, NMK = c.numask.p ? 1 : 0;
+  launch2t_fn fn = get_launch2t(c.MK, NU, F, NMK);
+  occ2t_fn occ = get_occ2t(c.MK, NU, F, NMK);
+  if (!fn || !occ) return DN_OK;
+  P2T p;
+  memset(&p, 0, sizeof(p));
+  int nf = 0;
+  p.fld[nf++] = c.u;
+  if (NU) p.fld[nf++] = c.nu;
+  if (F) p.fld[nf++] = c.f;
+  if (NMK) p.fld[nf++] = c.numask;
+  for (int i = 0; i < c.nmasks; ++i) { p.fld[nf++] = c.mk[i].m; p.mval[i] = c.mk[i].v; }
+  if (c.MK == 4) p.fld[nf++] = c.mk[0].vf;
+  Plan2T pl = plan2t(g, nf, sms, occ);
+  if (!pl.ok) { cudaGetLastError(); return DN_OK; }
+  if (pl.grid > 0x7fffffffLL) return DN_OK;
+  if (!workspace || wsb < ws_bytes_for_grid(pl.grid))
+    return fail(DN_EWORKSPACE, "workspace too small: %zu < %zu", wsb, ws_bytes_for_grid(pl.grid));
+  if ((uintptr_t)workspace % 16) return fail(DN_EWORKSPACE, "workspace must be 16-byte aligned");
+  p.nf = nf;
+  p.B = g->batch; p.nx = g->nx; p.ny = g->ny;
+  p.R = pl.R; p.nchunks = pl.nchunks; p.S = pl.S;
+  const float kx = c.k.kx, ky = c.k.ky, kf = c.k.kf, t = c.k.t;
+  p.k2.kx = make_float2(kx, kx); p.k2.ky = make_float2(ky, ky); p.k2.t = make_float2(t, t);
+  p.k2.kxt = make_float2(kx * t, kx * t); p.k2.kyt = make_float2(ky * t, ky * t);
+  p.k2.nkf = make_float2(-kf, -kf); p.k2.nkft = make_float2(-kf * t, -kf * t);
+  p.k2.nkftt = make_float2(-kf * t * t, -kf * t * t);
+  p.k2.c0x_const = make_float2(4.f * kx, 4.f * kx); p.k2.c0y_const = make_float2(4.f * ky, 4.f * ky);
+  p.grad = grad;
+  p.red.counter = (unsigned int*)workspace;
+  p.red.partials = (double*)((char*)workspace + 64);
+  p.red.loss_out = loss_out; p.red.loss_f32 = loss_f32;
+  p.mode = mode;
+  *handled = true;
+  return check_cuda(fn(p, dim3((unsigned)pl.grid), dim3(pl.threads), pl.smem, (cudaStream_t)stream),
+                    "fem2d_tma launch");
+}
+
 static int run2d(const Common& c, const dn_geom* g, float* grad, float* grad_nu, int mode,
                  int mask_input, void* workspace, size_t wsb, double* loss_out, float* loss_f32,
                  void* stream, int sms) {
+  if (!grad_nu && mask_input) {   // streaming path: common aligned cases (the rest stays on k_fem2d)
+    bool handled = false;
+    int rc = run2t(c, g, grad, mode, workspace, wsb, loss_out, loss_f32, stream, sms, &handled);
+    if (rc != DN_OK || handled) return rc;
+  }
   bool vec4 = c.vec4 && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)grad_nu % 16 == 0);
   Plan2D pl = plan2d(g, vec4, sms);
   if (!workspace || wsb < ws_bytes_for_grid(pl.grid))
@@ -228,6 +325,8 @@ size_t dn_fem_workspace_bytes(const dn_geom* g) {
       Plan2D pl = plan2d(g, v == 1, sms);
       if (pl.nitems > worst) worst = pl.nitems;
     }
+    const long long t2 = (long long)g->batch * ((g->ny + 3) / 4);   // streaming path, R >= 4
+    if (t2 > worst) worst = t2;
   } else {
     worst = plan3d_max_ctas(g);
   }

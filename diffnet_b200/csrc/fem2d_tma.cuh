@@ -1,0 +1,439 @@
+// fem2d_tma.cuh -- the streaming 2-D Q1 Poisson energy/residual + adjoint kernel (sm_100a).
+//
+// Same operator as fem2d.cuh (which stays as the general path: odd sizes, unaligned views,
+// f at Gauss points, d/dnu), restructured for the B200 memory system:
+//
+//   * A CTA owns one chunk of R node rows of one image at FULL row width; thread t owns the four
+//     nodes x0 = 4t .. 4t+3 of every row and the four elements to their right.
+//   * Node rows of all NF input fields travel HBM -> shared memory through a ring of S stages
+//     filled by bulk-async copies (cp.async.bulk, SASS UBLKCP) that complete on one mbarrier per
+//     stage.  The bytes in flight live in shared memory, not in registers: S rows x NF fields per
+//     CTA, 6-8 CTAs per SM, independent of how far the arithmetic has got.
+//   * Each node row is read from shared memory exactly once (one 16-byte load per field plus the
+//     right neighbour), masked, and reduced to its x-sums / x-differences, which serve both the
+//     element row above and the one below.  The element math is the closed form of DESIGN.md 4
+//     evaluated on float2 PAIRS of elements with FFMA2/FADD2/FMUL2 (two elements per issue slot).
+//   * Gradient gather without atomics: contributions to the top nodes are completed by one
+//     shuffle from the left lane (one shared-memory word across warp seams), contributions to
+//     the bottom nodes are carried in registers to the next row.  One __syncthreads per row
+//     releases the consumed ring stage and publishes the seam words.
+//   * Chunk seams: one halo row above and below is re-read (from L2) and the element row above
+//     the chunk recomputed; (R+2)/R reads, (R+1)/R arithmetic.
+#pragma once
+#include "dn_common.cuh"
+
+namespace dn {
+
+#define DN_T2_MAXF 8        // u, nu, f, numask, masks[3] | mask+value_field
+#define DN_T2_MAXT 512      // threads per CTA -> nx <= 2048
+
+// Packed constants of one launch (see prepare(): kx, ky carry S c_k W (2/h)^2 / 64, kf = S c_f W / 16)
+struct K2 {
+  float2 kx, ky, kxt, kyt, t, nkf, nkft, nkftt, c0x_const, c0y_const;
+};
+
+struct P2T {
+  Field fld[DN_T2_MAXF];    // slot order: u, [nu], [f], [numask], masks..., [value field]
+  float mval[DN_MAX_MASKS];
+  int nf;
+  int B, nx, ny;
+  int R, nchunks, S;
+  K2 k2;                    // packed (pair-replicated) constants, read straight from the constant bank
+  float* grad;              // dense (B, ny, nx); nullable (forward only)
+  Reduce red;
+  int mode;                 // 0: loss = energy; 1: loss = sum(out^2) (residual form)
+};
+
+// ---- PTX wrappers: mbarrier + bulk async copy ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "DN_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DN_DONE;\n"
+      "bra DN_WAIT;\n"
+      "DN_DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- float2 helpers (FADD2 / FMUL2 / FFMA2) --------------------------------------------------
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));   // the negation folds into the operand modifier
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// x-sums and x-differences of one masked node row: s[e] = v[e] + v[e+1], d[e] = v[e+1] - v[e]
+struct RowSD {
+  float2 s01, s23, d01, d23;
+};
+__device__ __forceinline__ RowSD row_sd(const float (&v)[5]) {
+  RowSD o;
+  o.s01 = f2(v[0] + v[1], v[1] + v[2]);
+  o.s23 = f2(v[2] + v[3], v[3] + v[4]);
+  o.d01 = f2(v[1] - v[0], v[2] - v[1]);
+  o.d23 = f2(v[3] - v[2], v[4] - v[3]);
+  return o;
+}
+
+
+// Two Q1 elements at once.  Inputs: x-sums/differences of u (top st,dt / bottom sb,db), of nu and
+// of f.  Outputs: energy pair E and the nodal gradient pairs ga (top-left), gb (top-right),
+// gc (bottom-left), gd (bottom-right).  Quadratic part in the half-gradient convention
+// q = (1/2) dEq/dA, so E = sum A (q - b) and g = q + (q - b).
+template <bool HAS_NU, bool HAS_F>
+__device__ __forceinline__ float2 elem_pair(const K2& k, float2 st, float2 dt, float2 sb, float2 db,
+                                            float2 nst, float2 ndt, float2 nsb, float2 ndb,
+                                            float2 fst, float2 fdt, float2 fsb, float2 fdb,
+                                            float2 vw, float2& ga, float2& gb, float2& gc,
+                                            float2& gd) {
+  const float2 Ae = sub2(sb, st), Ax = add2(dt, db), Axe = sub2(db, dt);
+  float2 c0x, c0y, qx, qe, qxe;
+  const float2 tAxe = mul2(k.t, Axe);
+  if constexpr (HAS_NU) {
+    const float2 C0 = add2(nst, nsb), Ce = sub2(nsb, nst), Cx = add2(ndt, ndb);
+    c0x = mul2(k.kx, C0);
+    c0y = mul2(k.ky, C0);
+    const float2 c1x = mul2(k.kxt, Ce), c1y = mul2(k.kyt, Cx);
+    qx = fma2(c0x, Ax, mul2(c1x, Axe));
+    qe = fma2(c0y, Ae, mul2(c1y, Axe));
+    qxe = fma2(add2(c0x, c0y), tAxe, fma2(c1x, Ax, mul2(c1y, Ae)));
+  } else {
+    // nu == 1: C0 = 4 (times the validity weight of the element), Cx = Ce = 0
+    c0x = mul2(k.c0x_const, vw);
+    c0y = mul2(k.c0y_const, vw);
+    qx = mul2(c0x, Ax);
+    qe = mul2(c0y, Ae);
+    qxe = mul2(add2(c0x, c0y), tAxe);
+  }
+  float2 E, g0, gx, ge, gxe;
+  if constexpr (HAS_F) {
+    const float2 A0 = add2(st, sb);
+    const float2 nb0 = mul2(k.nkf, add2(fst, fsb));        // -kf B0
+    const float2 nbx = mul2(k.nkft, add2(fdt, fdb));       // -kf t Bxi
+    const float2 nbe = mul2(k.nkft, sub2(fsb, fst));       // -kf t Beta
+    const float2 nbxe = mul2(k.nkftt, sub2(fdb, fdt));     // -kf t^2 Bxieta
+    const float2 tx = add2(qx, nbx), te = add2(qe, nbe), txe = add2(qxe, nbxe);
+    E = fma2(A0, nb0, fma2(Ax, tx, fma2(Ae, te, mul2(Axe, txe))));
+    g0 = nb0; gx = add2(qx, tx); ge = add2(qe, te); gxe = add2(qxe, txe);
+    const float2 m0 = sub2(g0, ge), m1 = add2(g0, ge), n0 = sub2(gx, gxe), n1 = add2(gx, gxe);
+    ga = sub2(m0, n0); gb = add2(m0, n0); gc = sub2(m1, n1); gd = add2(m1, n1);
+  } else {
+    E = fma2(Ax, qx, fma2(Ae, qe, mul2(Axe, qxe)));
+    gx = add2(qx, qx); ge = add2(qe, qe); gxe = add2(qxe, qxe);
+    const float2 n0 = sub2(gx, gxe), n1 = add2(gx, gxe);
+    // m0 = -ge, m1 = +ge
+    ga = sub2(f2(-ge.x, -ge.y), n0); gb = sub2(n0, ge); gc = sub2(ge, n1); gd = add2(ge, n1);
+  }
+  return E;
+}
+
+// Per-thread state of one masked node row: x-sums / x-differences of u, nu, f and the 0/1
+// "free node" multipliers (0 where a Dirichlet mask fired).
+struct Row2T {
+  RowSD u, n, f;
+  float2 keep01, keep23;
+};
+// Gradient accumulators of one node row: own nodes 0..3 and the right neighbour's node 0.
+struct Acc2T {
+  float2 a01, a23;
+  float a4;
+};
+
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK>
+struct Fem2T {
+  static constexpr int NF = 1 + (HAS_NU ? 1 : 0) + (HAS_F ? 1 : 0) + (NUMASK ? 1 : 0) + NM + (VF ? 1 : 0);
+  static constexpr int F_U = 0, F_NU = 1, F_F = F_NU + (HAS_NU ? 1 : 0), F_NM = F_F + (HAS_F ? 1 : 0),
+                       F_M = F_NM + (NUMASK ? 1 : 0), F_VF = F_M + NM;
+
+  // Read one node row from its ring stage (own 4 nodes + right neighbour of every field), apply
+  // the Dirichlet conditions (array order: later masks win) and the nu mask, reduce to x-sums.
+  static __device__ __forceinline__ void load_row(const P2T& p, const float* __restrict__ sp, int nx,
+                                                  bool has_right, Row2T& o) {
+    float v[NF][5];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const float* q = sp + f * nx;
+      const float4 t = *reinterpret_cast<const float4*>(q);
+      const float h = q[4];            // in-bounds of the ring for every thread (padded), masked below
+      v[f][0] = t.x; v[f][1] = t.y; v[f][2] = t.z; v[f][3] = t.w; v[f][4] = has_right ? h : 0.f;
+    }
+    float ub[5], nb[5], fb[5], kp[4];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      float u = v[F_U][e];
+      bool fx = false;
+#pragma unroll
+      for (int m = 0; m < NM; ++m) {
+        const bool hit = v[F_M + m][e] > 0.5f;
+        u = hit ? (VF ? v[F_VF][e] : p.mval[m]) : u;
+        fx = fx || hit;
+      }
+      ub[e] = u;
+      if (e < 4) kp[e] = fx ? 0.f : 1.f;
+      if constexpr (HAS_NU) {
+        float n = v[F_NU][e];
+        if constexpr (NUMASK) n = (v[F_NM][e] > 0.5f) ? 0.f : n;
+        nb[e] = n;
+      }
+      if constexpr (HAS_F) fb[e] = v[F_F][e];
+    }
+    o.keep01 = f2(kp[0], kp[1]);
+    o.keep23 = f2(kp[2], kp[3]);
+    o.u = row_sd(ub);
+    // the last element of a row does not exist: E and g are linear in (nu, f), so zeroing their
+    // x-sums/differences for that element removes it (nu == 1 uses the weight vw instead)
+    if constexpr (HAS_NU) {
+      o.n = row_sd(nb);
+      if (!has_right) { o.n.s23.y = 0.f; o.n.d23.y = 0.f; }
+    }
+    if constexpr (HAS_F) {
+      o.f = row_sd(fb);
+      if (!has_right) { o.f.s23.y = 0.f; o.f.d23.y = 0.f; }
+    }
+  }
+
+  // Element row between `top` and `bot`: adds its gradient to At (top nodes) and WRITES Ab
+  // (bottom nodes); returns the row's energy of this lane's 4 elements.
+  static __device__ __forceinline__ float elem_row(const K2& k, const Row2T& top, const Row2T& bot,
+                                                   float2 vw01, float2 vw23, Acc2T& At, Acc2T& Ab) {
+    float2 ga, gb, gc, gd;
+    const float2 E0 = elem_pair<HAS_NU, HAS_F>(k, top.u.s01, top.u.d01, bot.u.s01, bot.u.d01,
+                                              top.n.s01, top.n.d01, bot.n.s01, bot.n.d01,
+                                              top.f.s01, top.f.d01, bot.f.s01, bot.f.d01, vw01,
+                                              ga, gb, gc, gd);
+    At.a01 = add2(At.a01, ga);
+    At.a01.y += gb.x; At.a23.x += gb.y;
+    Ab.a01 = gc; Ab.a01.y += gd.x;
+    const float carry = gd.y;
+    const float2 E1 = elem_pair<HAS_NU, HAS_F>(k, top.u.s23, top.u.d23, bot.u.s23, bot.u.d23,
+                                              top.n.s23, top.n.d23, bot.n.s23, bot.n.d23,
+                                              top.f.s23, top.f.d23, bot.f.s23, bot.f.d23, vw23,
+                                              ga, gb, gc, gd);
+    At.a23 = add2(At.a23, ga);
+    At.a23.y += gb.x; At.a4 += gb.y;
+    Ab.a23 = gc; Ab.a23.x += carry; Ab.a23.y += gd.x;
+    Ab.a4 = gd.y;
+    const float2 Es = add2(E0, E1);
+    return Es.x + Es.y;
+  }
+};
+
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK>
+__global__ void __launch_bounds__(DN_T2_MAXT) k_fem2d_tma(const __grid_constant__ P2T p) {
+  using F = Fem2T<NM, VF, HAS_NU, HAS_F, NUMASK>;
+  constexpr int NF = F::NF;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_red[DN_T2_MAXT / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int nx = p.nx, S = p.S;
+  const int stage_floats = NF * nx;
+  float* ring = reinterpret_cast<float*>(smem_raw);                                   // [S][NF][nx] (+16 B pad)
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats + 4);  // [S]
+  float* seam = reinterpret_cast<float*>(full + S);                                   // [2][nw]
+
+  const int b = blockIdx.x / p.nchunks, ch = blockIdx.x - b * p.nchunks;
+  const int r_begin = ch * p.R, r_end = min(p.ny, r_begin + p.R);
+  const int j_first = max(r_begin - 1, 0), j_last = min(r_end, p.ny - 1);
+  const int nrows = j_last - j_first + 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(full + s, NF);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // ---- producer state: lane f < NF of warp 0 streams field f, one row (nx*4 bytes) per copy
+  const bool producer = (warp == 0) && (lane < NF);
+  const float* src = nullptr;
+  long long src_step = 0;
+  if (producer) {
+    const Field fl = p.fld[lane];
+    src = fl.p + (long long)b * fl.sb + (long long)j_first * fl.sy;
+    src_step = fl.sy;
+  }
+  const uint32_t row_bytes = (uint32_t)(nx * 4);
+  int issued = 0, ist = 0;               // rows issued so far, stage of the next issue
+  auto issue_row = [&]() {
+    if (producer) {
+      mbar_arrive_expect_tx(full + ist, row_bytes);
+      bulk_g2s(ring + ist * stage_floats + lane * nx, src, row_bytes, full + ist);
+      src += src_step;
+    }
+    ++issued;
+    ist = (ist + 1 == S) ? 0 : ist + 1;
+  };
+  {
+    const int n0 = min(S, nrows);
+    for (int r = 0; r < n0; ++r) issue_row();
+  }
+
+  const bool act = tid * 4 < nx;
+  const int x0 = act ? tid * 4 : 0;          // idle lanes of the last warp shadow lane 0 (results dropped)
+  const bool has_right = (x0 + 4) < nx;
+  const float2 vw01 = f2(1.f, 1.f);
+  const float2 vw23 = f2(1.f, has_right ? 1.f : 0.f);
+  const K2& k = p.k2;
+
+  double acc = 0.0;
+  int st = 0;                // stage of the row being consumed
+  uint32_t phase = 0;        // its mbarrier parity
+  const float* sbase = ring + x0;
+  float* gout = p.grad ? p.grad + ((long long)b * p.ny + j_first) * nx + x0 : nullptr;
+
+  // consume(): wait for the next node row, read it into `bot`, release its ring stage
+  auto wait_row = [&]() -> const float* {
+    mbar_wait(full + st, phase);
+    return sbase + st * stage_floats;
+  };
+  auto advance = [&]() {
+    ++st;
+    if (st == S) { st = 0; phase ^= 1u; }
+  };
+  // finalize(): node row `jr` is complete in A: add the left lane's share, mask, store
+  auto finalize = [&](const Acc2T& A, const Row2T& row, int jr, int par) {
+    float fromL = __shfl_up_sync(0xffffffffu, A.a4, 1);
+    if (lane == 0) fromL = (warp > 0) ? seam[par * nw + warp - 1] : 0.f;
+    if (jr >= r_begin) {
+      float2 g01 = A.a01, g23 = A.a23;
+      g01.x += fromL;
+      g01 = mul2(g01, row.keep01);
+      g23 = mul2(g23, row.keep23);
+      if (act) {
+        if (gout) *reinterpret_cast<float4*>(gout) = make_float4(g01.x, g01.y, g23.x, g23.y);
+        if (p.mode != 0) {
+          const float2 q = fma2(g01, g01, mul2(g23, g23));
+          acc += (double)(q.x + q.y);
+        }
+      }
+    }
+    if (gout) gout += nx;
+  };
+
+  Row2T rowA, rowB;
+  Acc2T accA, accB;
+  accA.a01 = accA.a23 = f2(0.f); accA.a4 = 0.f;
+  accB = accA;
+
+  // ---- first node row: nothing above it
+  {
+    const float* sp = wait_row();
+    F::load_row(p, sp, nx, has_right, rowA);
+    __syncthreads();
+    if (issued < nrows) issue_row();
+    advance();
+  }
+  // One step: `top` (registers) + the next node row -> element row; finalize the top node row.
+  auto step = [&](Row2T& top, Row2T& bot, Acc2T& At, Acc2T& Ab, int r) {
+    const float* sp = wait_row();
+    F::load_row(p, sp, nx, has_right, bot);
+    const float e = F::elem_row(k, top, bot, vw01, vw23, At, Ab);
+    const int jr = j_first + r - 1;                  // element row index == its top node row
+    if (p.mode == 0 && jr >= r_begin && act) acc += (double)e;
+    if (lane == 31) seam[(r & 1) * nw + warp] = At.a4;
+    __syncthreads();      // stage consumed by every thread; seam words of this row visible
+    if (issued < nrows) issue_row();
+    advance();
+    finalize(At, top, jr, r & 1);
+  };
+  int r = 1;
+  for (; r + 1 < nrows; r += 2) {
+    step(rowA, rowB, accA, accB, r);
+    step(rowB, rowA, accB, accA, r + 1);
+  }
+  const bool odd = r < nrows;         // one more row to consume; afterwards the live state is B
+  if (odd) step(rowA, rowB, accA, accB, r);
+
+  // ---- last node row of the image: no element row below it; its sum is already complete
+  if (r_end == p.ny) {
+    const Acc2T& A = odd ? accB : accA;
+    const Row2T& row = odd ? rowB : rowA;
+    if (lane == 31) seam[(nrows & 1) * nw + warp] = A.a4;
+    __syncthreads();
+    finalize(A, row, p.ny - 1, nrows & 1);
+  }
+
+  acc = warp_sum(acc);
+  if (lane == 0) s_red[warp] = acc;
+  __syncthreads();
+  double cta = 0.0;
+  if (tid == 0)
+    for (int w = 0; w < nw; ++w) cta += s_red[w];
+  __syncthreads();
+  finish_loss(p.red, cta, s_red);
+}
+
+// ---- dispatch (fem2d_tma_dispatch.cu) --------------------------------------------------------
+// MK encodes the Dirichlet set: 0..3 scalar-valued masks; 4 = one mask with a nodal value field.
+typedef cudaError_t (*launch2t_fn)(const P2T&, dim3, dim3, size_t, cudaStream_t);
+typedef int (*occ2t_fn)(int, size_t);
+launch2t_fn get_launch2t(int MK, int NU, int F, int NUMASK);
+occ2t_fn get_occ2t(int MK, int NU, int F, int NUMASK);
+
+constexpr int kMaxDynSmem = 226 * 1024;   // 227 KB per CTA minus the kernels' static shared memory
+
+template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+cudaError_t prep2t() {
+  // opt in to the full 227 KB of dynamic shared memory once per device
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  constexpr int NM = (MK == 4) ? 1 : MK;
+  e = cudaFuncSetAttribute(k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
+}
+
+template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+cudaError_t launch2t(const P2T& p, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+  constexpr int NM = (MK == 4) ? 1 : MK;
+  cudaError_t e = prep2t<MK, HAS_NU, HAS_F, NUMASK>();
+  if (e != cudaSuccess) return e;
+  k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK><<<grid, block, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+// resident CTAs per SM for a block of `threads` threads and `smem` bytes of dynamic shared memory
+template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+int occ2t(int threads, size_t smem) {
+  constexpr int NM = (MK == 4) ? 1 : MK;
+  if (prep2t<MK, HAS_NU, HAS_F, NUMASK>() != cudaSuccess) return 0;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &n, k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK>, threads, smem) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+}  // namespace dn

@@ -287,20 +287,51 @@ def test_full_size_properties():
         assert float(lc) == 0.0 and float(gc.abs().max()) == 0.0
         la, ga = fem.energy_loss_and_grad(u, nu=nu)
         assert torch.equal(la, loss) and torch.equal(ga, grad)            # deterministic
-        old = os.environ.get("DN_R_2D")
+        saved = {k: os.environ.get(k) for k in ("DN_R_2D", "DN_T2_R")}
         try:
             os.environ["DN_R_2D"] = "37"                                   # different row chunking
+            os.environ["DN_T2_R"] = "37"
             lb, gb = fem.energy_loss_and_grad(u, nu=nu)
         finally:
-            if old is None:
-                os.environ.pop("DN_R_2D")
-            else:
-                os.environ["DN_R_2D"] = old
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
         assert rel_scalar(lb, loss) < 1e-6 and torch.equal(gb, grad)       # seams are exact
         # batch samples are independent: sample 3 alone gives its slice of the gradient
         l1, g1 = fem.energy_loss_and_grad(u[3:4], nu=nu[3:4], reduction="sum")
         ls, gs = fem.energy_loss_and_grad(u, nu=nu, reduction="sum")
         assert torch.equal(g1[0], gs[3])
+
+
+def test_streaming_and_warp_paths_agree():
+    """The bulk-async streaming kernel (k_fem2d_tma) and the general warp-marching kernel
+    (k_fem2d) are two implementations of the same operator: same loss, same gradient, on the
+    aligned sizes both accept, for every Dirichlet-set / nu / f combination."""
+    B, H, W = 3, 70, 264
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W)
+    u, inputs, f = make_inputs(B, H, W, seed=5)
+    u, inputs, f = u.to(DEV), inputs.to(DEV), f.to(DEV)
+    nu, bc1, bc2 = inputs[:, 0:1], inputs[:, 1:2], inputs[:, 2:3]
+    bc3 = torch.zeros_like(bc1); bc3[:, :, 0, :] = 1
+    ubc = torch.randn_like(u)
+    cases = [dict(), dict(nu=nu), dict(f=f), dict(nu=nu, f=f, dirichlet=[(bc1, 1.0)]),
+             dict(nu=nu, f=f, dirichlet=[(bc1, 1.0), (bc2, 0.0)]),
+             dict(f=f, dirichlet=[(bc1, 1.0), (bc2, 0.0), (bc3, 0.25)]),
+             dict(nu=nu, f=f, dirichlet=[(bc2, ubc)]),
+             dict(nu=nu, f=f, nu_zero_mask=bc3, dirichlet=[(bc1, 1.0), (bc2, 0.0)])]
+    for kw in cases:
+        os.environ.pop("DN_2D_PATH", None)
+        ls, gs = fem.energy_loss_and_grad(u, **kw)
+        os.environ["DN_2D_PATH"] = "warp"
+        try:
+            lw, gw = fem.energy_loss_and_grad(u, **kw)
+        finally:
+            os.environ.pop("DN_2D_PATH", None)
+        assert rel_scalar(ls, lw) < 2e-6, (sorted(kw), float(ls), float(lw))
+        assert rel_l2(gs, gw) < 2e-6, sorted(kw)
+        assert torch.equal(gs == 0, gw == 0) or rel_l2(gs, gw) < 2e-6
 
 
 def test_errors_are_loud():
