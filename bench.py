@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (nsd, size, batch per GPU, bytes/DOF fwd+bwd, description)
     "poisson2d_param_256_b64": (2, 256, 64, 24, "Poisson 2D parametric 256x256 Q1, KL log-diffusivity, batch 64/GPU"),
+    "poisson2d_param_256_b16": (2, 256, 16, 24, "scaling probe: 256x256, batch 16"),
+    "poisson2d_param_256_b256": (2, 256, 256, 24, "scaling probe: 256x256, batch 256"),
+    "poisson2d_param_256_b1024": (2, 256, 1024, 24, "scaling probe: 256x256, batch 1024"),
     "poisson2d_512_b16": (2, 512, 16, 24, "Poisson 2D 512x512 Q1, batch 16/GPU (roofline point)"),
     "poisson2d_64_b1": (2, 64, 1, 24, "Poisson 2D non-parametric 64x64 (configs[0])"),
     "poisson3d_param_64_b16": (3, 64, 16, 20, "Poisson 3D parametric 64^3 Q1 hex, batch 16/GPU (u, source, sink, f)"),

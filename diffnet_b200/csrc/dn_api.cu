@@ -185,7 +185,7 @@ static size_t ws_bytes_for_grid(long long grid) { return 64 + 8 * (size_t)grid; 
 struct Plan2T { int ok, threads, S, R, nchunks, nf; long long grid; size_t smem; };
 
 static size_t smem_2t(int S, int nf, int nx, int threads) {
-  return (size_t)S * nf * nx * 4 + 16 + (size_t)S * 8 + 2 * (size_t)(threads / 32) * 4;
+  return (size_t)S * nf * 2 * nx * 4 + 16 + (size_t)S * 8 + 4 * (size_t)(threads / 32) * 4;
 }
 
 // Eligibility + launch shape.  `occ` (resident CTAs per SM) may be null: then only the upper
@@ -198,7 +198,7 @@ static Plan2T plan2t(const dn_geom* g, int nf, int sms, occ2t_fn occ) {
   pl.threads = (lanes + 31) / 32 * 32;
   if (pl.threads > DN_T2_MAXT) return pl;
   pl.nf = nf;
-  int S = env_int("DN_T2_STAGES", 4);
+  int S = env_int("DN_T2_STAGES", 2);           // stages of two node rows each
   if (S < 2) S = 2;
   if (S > 16) S = 16;
   while (S > 2 && smem_2t(S, nf, g->nx, pl.threads) > (size_t)64 * 1024) --S;   // keep >= 3 CTAs/SM
@@ -235,6 +235,7 @@ static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, void*
   if (path && !strcmp(path, "warp")) return DN_OK;
   if (!c.vec4 || c.fgp.p || ((uintptr_t)grad % 16 != 0)) return DN_OK;
   const int NU = c.nu.p ? 1 : 0, F = c.f.p ? 1 : 0, NMK = c.numask.p ? 1 : 0;
+  if (g->nx % 4 != 0 || g->nx / 4 > DN_T2_MAXT) return DN_OK;
   launch2t_fn fn = get_launch2t(c.MK, NU, F, NMK);
   occ2t_fn occ = get_occ2t(c.MK, NU, F, NMK);
   if (!fn || !occ) return DN_OK;
@@ -247,6 +248,8 @@ static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, void*
   if (NMK) p.fld[nf++] = c.numask;
   for (int i = 0; i < c.nmasks; ++i) { p.fld[nf++] = c.mk[i].m; p.mval[i] = c.mk[i].v; }
   if (c.MK == 4) p.fld[nf++] = c.mk[0].vf;
+  for (int i = 0; i < nf; ++i)
+    if (p.fld[i].sy != g->nx) return DN_OK;      // bulk copies take whole runs of rows
   Plan2T pl = plan2t(g, nf, sms, occ);
   if (!pl.ok) { cudaGetLastError(); return DN_OK; }
   if (pl.grid > 0x7fffffffLL) return DN_OK;

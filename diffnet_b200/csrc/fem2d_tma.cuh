@@ -20,6 +20,9 @@
 //   * Chunk seams: one halo row above and below is re-read (from L2) and the element row above
 //     the chunk recomputed; (R+2)/R reads, (R+1)/R arithmetic.
 #pragma once
+#include <cstdlib>
+#include <cstring>
+
 #include "dn_common.cuh"
 
 namespace dn {
@@ -66,6 +69,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// Programmatic dependent launch (a no-op for a grid launched without the attribute):
+// pdl_trigger() lets the NEXT grid in the stream begin launching while this one still runs;
+// pdl_wait() blocks until the PREVIOUS grid has completed and its memory is visible.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -175,12 +183,12 @@ struct Fem2T {
 
   // Read one node row from its ring stage (own 4 nodes + right neighbour of every field), apply
   // the Dirichlet conditions (array order: later masks win) and the nu mask, reduce to x-sums.
-  static __device__ __forceinline__ void load_row(const P2T& p, const float* __restrict__ sp, int nx,
+  static __device__ __forceinline__ void load_row(const P2T& p, const float* __restrict__ sp, int fstride,
                                                   bool has_right, Row2T& o) {
     float v[NF][5];
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-      const float* q = sp + f * nx;
+      const float* q = sp + f * fstride;
       const float4 t = *reinterpret_cast<const float4*>(q);
       const float h = q[4];            // in-bounds of the ring for every thread (padded), masked below
       v[f][0] = t.x; v[f][1] = t.y; v[f][2] = t.z; v[f][3] = t.w; v[f][4] = has_right ? h : 0.f;
@@ -246,55 +254,92 @@ struct Fem2T {
   }
 };
 
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK>
-__global__ void __launch_bounds__(DN_T2_MAXT) k_fem2d_tma(const __grid_constant__ P2T p) {
+// Loss epilogue for the streaming kernels: only warp 0 takes part (the other warps retire at
+// once).  Thread 0 publishes the CTA partial and draws a ticket; the warp that draws the last
+// one sums all partials in a fixed order (lane-strided, then an xor butterfly): bit-reproducible.
+__device__ __forceinline__ void finish_loss_w0(const Reduce& r, double cta_value) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  unsigned last = 0u;
+  if (lane == 0) {
+    __stcg(r.partials + blockIdx.x, cta_value);
+    __threadfence();
+    last = (atomicAdd(r.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  const unsigned n = gridDim.x;
+  double s = 0.0;
+  for (unsigned base = 0; base < n; base += 32 * 40) {   // up to 40 independent L2 loads per lane in flight
+    double v[40];
+#pragma unroll
+    for (int q = 0; q < 40; ++q) {
+      const unsigned i = base + q * 32 + lane;
+      v[q] = (i < n) ? __ldcg(r.partials + i) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 40; ++q) s += v[q];
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (r.loss_out) *r.loss_out = s;
+    if (r.loss_f32) *r.loss_f32 = (float)s;
+    *r.counter = 0u;   // self-reset: the workspace is ready for the next call
+  }
+}
+
+// TB = max threads per CTA, MINB = min resident CTAs per SM the register allocation must allow.
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ P2T p) {
   using F = Fem2T<NM, VF, HAS_NU, HAS_F, NUMASK>;
   constexpr int NF = F::NF;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ double s_red[DN_T2_MAXT / 32];
+  __shared__ double s_red[TB / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int nx = p.nx, S = p.S;
-  const int stage_floats = NF * nx;
-  float* ring = reinterpret_cast<float*>(smem_raw);                                   // [S][NF][nx] (+16 B pad)
+  const int stage_floats = NF * 2 * nx;                                               // 2 node rows per stage
+  float* ring = reinterpret_cast<float*>(smem_raw);                                   // [S][NF][2][nx] (+16 B pad)
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats + 4);  // [S]
-  float* seam = reinterpret_cast<float*>(full + S);                                   // [2][nw]
+  float* seam = reinterpret_cast<float*>(full + S);                                   // [2 parities][2 rows][nw]
 
   const int b = blockIdx.x / p.nchunks, ch = blockIdx.x - b * p.nchunks;
   const int r_begin = ch * p.R, r_end = min(p.ny, r_begin + p.R);
   const int j_first = max(r_begin - 1, 0), j_last = min(r_end, p.ny - 1);
-  const int nrows = j_last - j_first + 1;
+  const int nrows = j_last - j_first + 1;          // node rows streamed: >= 2
+  const int nst = (nrows + 1) >> 1;                // stages streamed (the last may hold one row)
 
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(full + s, NF);
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  // ---- producer state: lane f < NF of warp 0 streams field f, one row (nx*4 bytes) per copy
-  const bool producer = (warp == 0) && (lane < NF);
-  const float* src = nullptr;
-  long long src_step = 0;
-  if (producer) {
-    const Field fl = p.fld[lane];
-    src = fl.p + (long long)b * fl.sb + (long long)j_first * fl.sy;
-    src_step = fl.sy;
-  }
-  const uint32_t row_bytes = (uint32_t)(nx * 4);
-  int issued = 0, ist = 0;               // rows issued so far, stage of the next issue
-  auto issue_row = [&]() {
-    if (producer) {
-      mbar_arrive_expect_tx(full + ist, row_bytes);
-      bulk_g2s(ring + ist * stage_floats + lane * nx, src, row_bytes, full + ist);
-      src += src_step;
+  // ---- producer: thread 0 copies, per stage, two rows of every field (one bulk copy per field)
+  int issued = 0, ist = 0;
+  auto issue_stage = [&]() {
+    if (tid == 0) {
+      const int r0 = 2 * issued;
+      const int nr = min(2, nrows - r0);
+      const uint32_t row_bytes = (uint32_t)(nx * 4);
+      uint64_t* bar = full + ist;
+      float* dst = ring + ist * stage_floats;
+      mbar_arrive_expect_tx(bar, (uint32_t)(NF * nr) * row_bytes);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        // rows are contiguous in memory (stride_y == nx is an eligibility condition of this path)
+        const float* src = p.fld[f].p + (long long)b * p.fld[f].sb + (long long)(j_first + r0) * nx;
+        bulk_g2s(dst + f * 2 * nx, src, (uint32_t)nr * row_bytes, bar);
+      }
     }
     ++issued;
     ist = (ist + 1 == S) ? 0 : ist + 1;
   };
-  {
-    const int n0 = min(S, nrows);
-    for (int r = 0; r < n0; ++r) issue_row();
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(full + s, 1);
+    fence_mbar_init();
   }
+  pdl_wait();            // everything above overlaps the tail of the previous grid in the stream
+  {
+    const int n0 = min(S, nst);
+    for (int q = 0; q < n0; ++q) issue_stage();     // thread 0 only; the others just count
+  }
+  __syncthreads();                                   // barriers initialised before anyone waits
 
   const bool act = tid * 4 < nx;
   const int x0 = act ? tid * 4 : 0;          // idle lanes of the last warp shadow lane 0 (results dropped)
@@ -302,93 +347,102 @@ __global__ void __launch_bounds__(DN_T2_MAXT) k_fem2d_tma(const __grid_constant_
   const float2 vw01 = f2(1.f, 1.f);
   const float2 vw23 = f2(1.f, has_right ? 1.f : 0.f);
   const K2& k = p.k2;
+  const bool seam_in = (lane == 0) && (warp > 0);
 
   double acc = 0.0;
-  int st = 0;                // stage of the row being consumed
+  int st = 0;                // stage being consumed
   uint32_t phase = 0;        // its mbarrier parity
   const float* sbase = ring + x0;
   float* gout = p.grad ? p.grad + ((long long)b * p.ny + j_first) * nx + x0 : nullptr;
 
-  // consume(): wait for the next node row, read it into `bot`, release its ring stage
-  auto wait_row = [&]() -> const float* {
-    mbar_wait(full + st, phase);
-    return sbase + st * stage_floats;
+  // Node row `jr` is complete in A except for the share of the left neighbour: take it from the
+  // left lane now (across a warp seam it arrives through shared memory after the barrier).
+  auto close_row = [&](const Acc2T& A, const Row2T& row, float4& G) {
+    const float fromL = __shfl_up_sync(0xffffffffu, A.a4, 1);
+    float2 g01 = A.a01;
+    if (lane > 0) g01.x += fromL;
+    g01 = mul2(g01, row.keep01);
+    const float2 g23 = mul2(A.a23, row.keep23);
+    G = make_float4(g01.x, g01.y, g23.x, g23.y);
   };
-  auto advance = [&]() {
-    ++st;
-    if (st == S) { st = 0; phase ^= 1u; }
-  };
-  // finalize(): node row `jr` is complete in A: add the left lane's share, mask, store
-  auto finalize = [&](const Acc2T& A, const Row2T& row, int jr, int par) {
-    float fromL = __shfl_up_sync(0xffffffffu, A.a4, 1);
-    if (lane == 0) fromL = (warp > 0) ? seam[par * nw + warp - 1] : 0.f;
-    if (jr >= r_begin) {
-      float2 g01 = A.a01, g23 = A.a23;
-      g01.x += fromL;
-      g01 = mul2(g01, row.keep01);
-      g23 = mul2(g23, row.keep23);
-      if (act) {
-        if (gout) *reinterpret_cast<float4*>(gout) = make_float4(g01.x, g01.y, g23.x, g23.y);
-        if (p.mode != 0) {
-          const float2 q = fma2(g01, g01, mul2(g23, g23));
-          acc += (double)(q.x + q.y);
-        }
-      }
+  auto store_row = [&](float4 G, float keep0, float seam_v, int jr) {
+    if (seam_in) G.x += seam_v * keep0;
+    if (jr >= r_begin && act) {
+      if (gout) *reinterpret_cast<float4*>(gout + (long long)(jr - j_first) * nx) = G;
+      if (p.mode != 0) acc += (double)(G.x * G.x + G.y * G.y + G.z * G.z + G.w * G.w);
     }
-    if (gout) gout += nx;
   };
 
-  Row2T rowA, rowB;
+  Row2T rowA, rowB;          // even node rows of the chunk live in A, odd ones in B
   Acc2T accA, accB;
   accA.a01 = accA.a23 = f2(0.f); accA.a4 = 0.f;
   accB = accA;
 
-  // ---- first node row: nothing above it
-  {
-    const float* sp = wait_row();
-    F::load_row(p, sp, nx, has_right, rowA);
-    __syncthreads();
-    if (issued < nrows) issue_row();
-    advance();
+  for (int q = 0; q < nst; ++q) {
+    mbar_wait(full + st, phase);
+    const float* sp = sbase + st * stage_floats;
+    const int r0 = 2 * q;                              // even row of this stage (chunk-relative)
+    const bool has_odd = (r0 + 1) < nrows;
+    const int par = q & 1;
+    float4 G0 = make_float4(0.f, 0.f, 0.f, 0.f), G1 = G0;
+    float kp0 = 0.f, kp1 = 0.f, e = 0.f;
+
+    // ---- even row -> A; element row (B above, A below); node row r0-1 (B) closes
+    F::load_row(p, sp, 2 * nx, has_right, rowA);
+    if (q > 0) {
+      const float e0 = F::elem_row(k, rowB, rowA, vw01, vw23, accB, accA);
+      if (j_first + r0 - 1 >= r_begin) e += e0;
+      if (lane == 31) seam[(par * 2 + 0) * nw + warp] = accB.a4;
+      close_row(accB, rowB, G0);
+      kp0 = rowB.keep01.x;
+    }
+    // ---- odd row -> B; element row (A above, B below); node row r0 (A) closes
+    if (has_odd) {
+      F::load_row(p, sp + nx, 2 * nx, has_right, rowB);
+      const float e1 = F::elem_row(k, rowA, rowB, vw01, vw23, accA, accB);
+      if (j_first + r0 >= r_begin) e += e1;
+      if (lane == 31) seam[(par * 2 + 1) * nw + warp] = accA.a4;
+      close_row(accA, rowA, G1);
+      kp1 = rowA.keep01.x;
+    }
+    if (p.mode == 0 && act) acc += (double)e;
+    __syncthreads();      // stage consumed by every thread; seam words of both rows visible
+    if (issued < nst) issue_stage();
+    ++st;
+    if (st == S) { st = 0; phase ^= 1u; }
+    float s0 = 0.f, s1 = 0.f;
+    if (seam_in) {
+      s0 = seam[(par * 2 + 0) * nw + warp - 1];
+      s1 = seam[(par * 2 + 1) * nw + warp - 1];
+    }
+    if (q > 0) store_row(G0, kp0, s0, j_first + r0 - 1);
+    if (has_odd) store_row(G1, kp1, s1, j_first + r0);
   }
-  // One step: `top` (registers) + the next node row -> element row; finalize the top node row.
-  auto step = [&](Row2T& top, Row2T& bot, Acc2T& At, Acc2T& Ab, int r) {
-    const float* sp = wait_row();
-    F::load_row(p, sp, nx, has_right, bot);
-    const float e = F::elem_row(k, top, bot, vw01, vw23, At, Ab);
-    const int jr = j_first + r - 1;                  // element row index == its top node row
-    if (p.mode == 0 && jr >= r_begin && act) acc += (double)e;
-    if (lane == 31) seam[(r & 1) * nw + warp] = At.a4;
-    __syncthreads();      // stage consumed by every thread; seam words of this row visible
-    if (issued < nrows) issue_row();
-    advance();
-    finalize(At, top, jr, r & 1);
-  };
-  int r = 1;
-  for (; r + 1 < nrows; r += 2) {
-    step(rowA, rowB, accA, accB, r);
-    step(rowB, rowA, accB, accA, r + 1);
-  }
-  const bool odd = r < nrows;         // one more row to consume; afterwards the live state is B
-  if (odd) step(rowA, rowB, accA, accB, r);
 
   // ---- last node row of the image: no element row below it; its sum is already complete
   if (r_end == p.ny) {
-    const Acc2T& A = odd ? accB : accA;
-    const Row2T& row = odd ? rowB : rowA;
-    if (lane == 31) seam[(nrows & 1) * nw + warp] = A.a4;
+    const bool lastB = (nrows & 1) == 0;             // the last streamed row is odd -> lives in B
+    const Acc2T& A = lastB ? accB : accA;
+    const Row2T& row = lastB ? rowB : rowA;
+    const int par = nst & 1;
+    if (lane == 31) seam[(par * 2) * nw + warp] = A.a4;
+    float4 G;
+    close_row(A, row, G);
     __syncthreads();
-    finalize(A, row, p.ny - 1, nrows & 1);
+    const float sv = seam_in ? seam[(par * 2) * nw + warp - 1] : 0.f;
+    store_row(G, row.keep01.x, sv, p.ny - 1);
   }
 
+  // all streaming done: the next grid in the stream may start launching behind our epilogue
+  // (its own pdl_wait() still holds it until this grid has completed and flushed)
+  pdl_trigger();
   acc = warp_sum(acc);
   if (lane == 0) s_red[warp] = acc;
   __syncthreads();
   double cta = 0.0;
   if (tid == 0)
     for (int w = 0; w < nw; ++w) cta += s_red[w];
-  __syncthreads();
-  finish_loss(p.red, cta, s_red);
+  finish_loss_w0(p.red, cta);
 }
 
 // ---- dispatch (fem2d_tma_dispatch.cu) --------------------------------------------------------
@@ -398,18 +452,33 @@ typedef int (*occ2t_fn)(int, size_t);
 launch2t_fn get_launch2t(int MK, int NU, int F, int NUMASK);
 occ2t_fn get_occ2t(int MK, int NU, int F, int NUMASK);
 
+// DN_PDL=0 disables programmatic dependent launch (default on)
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DN_PDL"); v = (e && *e == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 constexpr int kMaxDynSmem = 226 * 1024;   // 227 KB per CTA minus the kernels' static shared memory
+
+// One register budget (<= 128 registers, CTAs of up to 512 threads).  A tighter variant
+// (<= 96 registers, 10 instead of 8 resident 64-thread CTAs per SM) measured 10% SLOWER on
+// 256^2 x 64: more CTAs per wave means shorter row chunks and more seam work (profiles/).
+template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+struct Kern2T {
+  static constexpr int NM = (MK == 4) ? 1 : MK;
+  static auto get() { return k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK, DN_T2_MAXT, 1>; }
+};
 
 template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
 cudaError_t prep2t() {
-  // opt in to the full 227 KB of dynamic shared memory once per device
+  // opt in to the full dynamic shared memory once per device
   static bool done[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  constexpr int NM = (MK == 4) ? 1 : MK;
-  e = cudaFuncSetAttribute(k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK>,
+  e = cudaFuncSetAttribute(Kern2T<MK, HAS_NU, HAS_F, NUMASK>::get(),
                            cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
   if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
   return e;
@@ -417,21 +486,25 @@ cudaError_t prep2t() {
 
 template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
 cudaError_t launch2t(const P2T& p, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
-  constexpr int NM = (MK == 4) ? 1 : MK;
   cudaError_t e = prep2t<MK, HAS_NU, HAS_F, NUMASK>();
   if (e != cudaSuccess) return e;
-  k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK><<<grid, block, smem, s>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  if (pdl_enabled()) { cfg.attrs = at; cfg.numAttrs = 1; }
+  return cudaLaunchKernelEx(&cfg, Kern2T<MK, HAS_NU, HAS_F, NUMASK>::get(), p);
 }
 
 // resident CTAs per SM for a block of `threads` threads and `smem` bytes of dynamic shared memory
 template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
 int occ2t(int threads, size_t smem) {
-  constexpr int NM = (MK == 4) ? 1 : MK;
   if (prep2t<MK, HAS_NU, HAS_F, NUMASK>() != cudaSuccess) return 0;
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &n, k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK>, threads, smem) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern2T<MK, HAS_NU, HAS_F, NUMASK>::get(),
+                                                    threads, smem) != cudaSuccess)
     return 0;
   return n;
 }

@@ -1,5 +1,5 @@
 // Instantiation list of k_fem2d_tma: X(MK, HAS_NU, HAS_F, NUMASK).
-//   MK  Dirichlet set (0..3 scalar-valued masks, 4 = one mask with a nodal value field)
+//   MK    Dirichlet set (0..3 scalar-valued masks, 4 = one mask with a nodal value field)
 #pragma once
 #define DN2T_COMBOS(X, MK)                                                       \
   X(MK, false, false, false) X(MK, false, true, false) X(MK, true, false, false) \

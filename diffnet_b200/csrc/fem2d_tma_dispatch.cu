@@ -9,8 +9,8 @@ DN2T_ALL(DN_EXT)
 #undef DN_EXT
 
 launch2t_fn get_launch2t(int MK, int NU, int F, int NUMASK) {
-#define DN_CASE(MK_, NU_, F_, NMK_)                                                \
-  if (MK == MK_ && NU == (int)NU_ && F == (int)F_ && NUMASK == (int)NMK_)          \
+#define DN_CASE(MK_, NU_, F_, NMK_)                                                          \
+  if (MK == MK_ && NU == (int)NU_ && F == (int)F_ && NUMASK == (int)NMK_)     \
     return &launch2t<MK_, NU_, F_, NMK_>;
   DN2T_ALL(DN_CASE)
 #undef DN_CASE
@@ -18,8 +18,8 @@ launch2t_fn get_launch2t(int MK, int NU, int F, int NUMASK) {
 }
 
 occ2t_fn get_occ2t(int MK, int NU, int F, int NUMASK) {
-#define DN_CASE(MK_, NU_, F_, NMK_)                                                \
-  if (MK == MK_ && NU == (int)NU_ && F == (int)F_ && NUMASK == (int)NMK_)          \
+#define DN_CASE(MK_, NU_, F_, NMK_)                                                          \
+  if (MK == MK_ && NU == (int)NU_ && F == (int)F_ && NUMASK == (int)NMK_)     \
     return &occ2t<MK_, NU_, F_, NMK_>;
   DN2T_ALL(DN_CASE)
 #undef DN_CASE
