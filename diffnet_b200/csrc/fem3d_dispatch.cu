@@ -6,6 +6,14 @@
 #include "fem3d_combos.h"
 
 namespace dn {
+long long plan3t_max_ctas(const dn_geom* g);
+int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, const Field& numask,
+          const Mask* mk, int nmasks, int MK, const Consts& k, bool vec4, const dn_geom* g, float* grad,
+          int mode, int mask_input, void* workspace, size_t wsb, double* loss_out, float* loss_f32,
+          void* stream, int sms, bool* handled);
+}
+
+namespace dn {
 #define DN_EXT(V, MK, NU, FM, NMK) \
   extern template cudaError_t launch3d<V, MK, NU, FM, NMK>(const P3D&, dim3, dim3, size_t, cudaStream_t);
 DN3D_ALL(DN_EXT)
@@ -70,6 +78,9 @@ long long plan3d_max_ctas(const dn_geom* g) {
     Plan3D pl = plan3d(g, v == 1, 148);
     if (pl.grid > worst) worst = pl.grid;
   }
+  // streaming path: tiles own >= 1 row... bounded by its planner's minimum chunk (ZCmin >= 1)
+  const long long t3 = plan3t_max_ctas(g);
+  if (t3 > worst) worst = t3;
   return worst;
 }
 
@@ -77,6 +88,13 @@ int run3d(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
           const Mask* mk, int MK, const Consts& k, const Rule& rule, bool vec4, const dn_geom* g,
           float* grad, int mode, int mask_input, void* workspace, size_t wsb, double* loss_out,
           float* loss_f32, void* stream, int sms) {
+  {   // streaming path: common aligned cases (the rest stays on k_fem3d)
+    bool handled = false;
+    const int nmasks = (MK == 4) ? 1 : MK;
+    int rc = run3t(u, nu, f, fgp, numask, mk, nmasks, MK, k, vec4, g, grad, mode, mask_input, workspace,
+                   wsb, loss_out, loss_f32, stream, sms, &handled);
+    if (rc != DN_OK || handled) return rc;
+  }
   vec4 = vec4 && ((uintptr_t)grad % 16 == 0);
   Plan3D pl = plan3d(g, vec4, sms);
   if (pl.TY < 1 || (pl.nty > 1 && pl.TY < 2) || (pl.ntx > 1 && pl.LX < 2))

@@ -1,0 +1,438 @@
+// fem3d_tma.cuh -- the streaming 3-D Q1 (hex) Poisson energy/residual + adjoint kernel (sm_100a).
+//
+// Same operator as fem3d.cuh (which stays as the general path: odd sizes, unaligned or
+// non-contiguous views, nx > 256, f at Gauss points), rebuilt around the two facts the profile of
+// the first kernel showed: the 3-D element is ISSUE-bound (about 8x the arithmetic of the 2-D
+// one per byte), and its loads must not sit in registers.
+//
+//   * A CTA owns TY node rows (full width) of a chunk of ZC node planes and marches up in z.
+//     Plane tiles (TY+2 rows x nx, one contiguous run of memory per field) travel HBM -> shared
+//     memory through a ring of S stages filled by bulk-async copies (cp.async.bulk, SASS UBLKCP)
+//     completing on one mbarrier per stage.
+//   * Thread (r, lx) owns ONE PAIR of hexahedra: element row r of the tile, columns 2lx, 2lx+1,
+//     in every layer.  All element arithmetic is packed f32x2 (FFMA2/FADD2/FMUL2): the two
+//     elements of the pair share every issue slot.
+//   * The 2x2x2 modal (Hadamard) transform is hierarchical: x-sums/differences per node row,
+//     y-stage per element face, z-stage per element.  The face below an element is the face above
+//     the previous one: it is carried in registers, so each plane is read once per thread.
+//     The transposed transform (modal gradient -> nodes) is hierarchical the same way and the
+//     z-carry of the gradient is kept in row (sum, difference) space.
+//   * Gradient gather without atomics: per plane each thread publishes its lower-row partial sums
+//     to shared memory; after ONE __syncthreads (which also releases the consumed ring stage) the
+//     owner of each node row adds the three neighbour shares, masks Dirichlet nodes and stores.
+//   * Seams: one halo row above/below the tile and one halo plane below/above the chunk are
+//     re-read (L2) and their elements recomputed: (TY+1)/TY x (ZC+1)/ZC arithmetic.
+#pragma once
+#include "fem2d_tma.cuh"
+
+namespace dn {
+
+#define DN_T3_MAXT 512      // threads per CTA (<= 128 registers each)
+
+// pair-replicated constants (half-gradient convention: k, not 2k)
+struct K3 {
+  float2 kx, ky, kz, kxt, kyt, kzt, kxtt, kytt, kztt, t, tt, nkf, nkft, nkftt, nkfttt, c0x, c0y, c0z;
+};
+
+struct P3T {
+  Field fld[DN_T2_MAXF];    // slot order: u, [nu], [f], [numask], masks..., [value field]
+  float mval[DN_MAX_MASKS];
+  int nf;
+  int B, nx, ny, nz;
+  int LX, TY, nty, ZC, nzc, S;   // lanes per row (nx/2), owned rows per tile, tiles, planes per chunk, chunks, stages
+  int zloss_lo, zloss_hi;         // element layers whose energy counts (z-slab ownership)
+  K3 k3;
+  float* grad;                    // dense (B, nz, ny, nx); nullable
+  Reduce red;
+  int mode;                       // 0: loss = energy; 1: loss = sum(out^2)
+};
+
+// Face modes of one field for a pair of elements; index bit0 = x, bit1 = y; set bit = difference.
+struct Face {
+  float2 m0, m1, m2, m3;
+};
+
+// one direction of the stiffness form:  q = M(c) P  (half gradient),  P = 4 modal coefficients
+// carrying the differentiated direction, c = the 4 nu modes that survive the integration.
+// Q1,Q2,Q3 = t P1, t P2, t P3 and Q33 = t^2 P3 are shared between directions by the caller.
+__device__ __forceinline__ void dir_q(float2 d0, float2 d1, float2 d2, float2 d3, float2 P0, float2 P1,
+                                      float2 P2, float2 P3, float2 Q1, float2 Q2, float2 Q3, float2 Q33,
+                                      float2& q0, float2& q1, float2& q2, float2& q3) {
+  q0 = fma2(d0, P0, fma2(d1, P1, fma2(d2, P2, mul2(d3, P3))));
+  q1 = fma2(d0, Q1, fma2(d1, P0, fma2(d2, Q3, mul2(d3, P2))));
+  q2 = fma2(d0, Q2, fma2(d1, Q3, fma2(d2, P0, mul2(d3, P1))));
+  q3 = fma2(d0, Q33, fma2(d1, Q2, fma2(d2, Q1, mul2(d3, P0))));
+}
+
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK>
+struct Fem3T {
+  static constexpr int NF = 1 + (HAS_NU ? 1 : 0) + (HAS_F ? 1 : 0) + (NUMASK ? 1 : 0) + NM + (VF ? 1 : 0);
+  static constexpr int F_U = 0, F_NU = 1, F_F = F_NU + (HAS_NU ? 1 : 0), F_NM = F_F + (HAS_F ? 1 : 0),
+                       F_M = F_NM + (NUMASK ? 1 : 0), F_VF = F_M + NM;
+
+  // x-stage of one node row (3 nodes -> 2 elements): s = (v0+v1, v1+v2), d = (v1-v0, v2-v1)
+  static __device__ __forceinline__ void xs(const float (&v)[3], float2& s, float2& d) {
+    s = f2(v[0] + v[1], v[1] + v[2]);
+    d = f2(v[1] - v[0], v[2] - v[1]);
+  }
+
+  // Read node rows a (local row r) and b (r+1) of one plane from its ring stage, apply the
+  // Dirichlet conditions / nu mask, and reduce to the face modes of u, nu, f.
+  // `sp` points at (row r, column x0) of field 0; `fstride` floats between fields.
+  static __device__ __forceinline__ void load_faces(const P3T& p, const float* __restrict__ sp, int nx,
+                                                    int fstride, bool has_right, Face& Uu, Face& Un,
+                                                    Face& Uf, float2& keep_a, float2& keep_b) {
+    float2 su[2], du[2], sn[2], dn_[2], sf[2], df[2];
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      float v[NF][3];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const float* q = sp + f * fstride + row * nx;
+        const float2 t = *reinterpret_cast<const float2*>(q);
+        const float h = q[2];          // in-bounds of the ring for every thread (padded), masked below
+        v[f][0] = t.x; v[f][1] = t.y; v[f][2] = has_right ? h : 0.f;
+      }
+      float ub[3], nb[3], fb[3], kp[2];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        float u = v[F_U][e];
+        bool fx = false;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          const bool hit = v[F_M + m][e] > 0.5f;
+          u = hit ? (VF ? v[F_VF][e] : p.mval[m]) : u;
+          fx = fx || hit;
+        }
+        ub[e] = u;
+        if (e < 2) kp[e] = fx ? 0.f : 1.f;
+        if constexpr (HAS_NU) {
+          float n = v[F_NU][e];
+          if constexpr (NUMASK) n = (v[F_NM][e] > 0.5f) ? 0.f : n;
+          nb[e] = n;
+        }
+        if constexpr (HAS_F) fb[e] = v[F_F][e];
+      }
+      if (row == 0) keep_a = f2(kp[0], kp[1]); else keep_b = f2(kp[0], kp[1]);
+      xs(ub, su[row], du[row]);
+      // the last element of a row does not exist: E and g are linear in (nu, f), so zeroing
+      // their x-sums/differences removes it (nu == 1 uses the weight vw instead)
+      if constexpr (HAS_NU) {
+        xs(nb, sn[row], dn_[row]);
+        if (!has_right) { sn[row].y = 0.f; dn_[row].y = 0.f; }
+      }
+      if constexpr (HAS_F) {
+        xs(fb, sf[row], df[row]);
+        if (!has_right) { sf[row].y = 0.f; df[row].y = 0.f; }
+      }
+    }
+    Uu.m0 = add2(su[0], su[1]); Uu.m1 = add2(du[0], du[1]);
+    Uu.m2 = sub2(su[1], su[0]); Uu.m3 = sub2(du[1], du[0]);
+    if constexpr (HAS_NU) {
+      Un.m0 = add2(sn[0], sn[1]); Un.m1 = add2(dn_[0], dn_[1]);
+      Un.m2 = sub2(sn[1], sn[0]); Un.m3 = sub2(dn_[1], dn_[0]);
+    }
+    if constexpr (HAS_F) {
+      Uf.m0 = add2(sf[0], sf[1]); Uf.m1 = add2(df[0], df[1]);
+      Uf.m2 = sub2(sf[1], sf[0]); Uf.m3 = sub2(df[1], df[0]);
+    }
+  }
+
+  // One pair of hexahedra between the lower faces L* and the upper faces U*.  Returns the energy
+  // pair; gLo / gUp = gradient w.r.t. the face modes of u on the lower / upper face.
+  static __device__ __forceinline__ float2 elem_pair(const K3& k, const Face& Lu, const Face& Uu,
+                                                     const Face& Ln, const Face& Un, const Face& Lf,
+                                                     const Face& Uf, float2 vw, Face& gLo, Face& gUp) {
+    // z-stage: modes m = 4*zbit + 2*ybit + xbit
+    const float2 u1 = add2(Lu.m1, Uu.m1), u2 = add2(Lu.m2, Uu.m2), u3 = add2(Lu.m3, Uu.m3);
+    const float2 u4 = sub2(Uu.m0, Lu.m0), u5 = sub2(Uu.m1, Lu.m1), u6 = sub2(Uu.m2, Lu.m2),
+                 u7 = sub2(Uu.m3, Lu.m3);
+    const float2 Q3 = mul2(k.t, u3), Q5 = mul2(k.t, u5), Q6 = mul2(k.t, u6), Q7 = mul2(k.t, u7),
+                 Q77 = mul2(k.tt, u7);
+    float2 qx0, qx1, qx2, qx3, qy0, qy1, qy2, qy3, qz0, qz1, qz2, qz3;
+    if constexpr (HAS_NU) {
+      const float2 C0 = add2(Ln.m0, Un.m0), C1 = add2(Ln.m1, Un.m1), C2 = add2(Ln.m2, Un.m2),
+                   C3 = add2(Ln.m3, Un.m3);
+      const float2 C4 = sub2(Un.m0, Ln.m0), C5 = sub2(Un.m1, Ln.m1), C6 = sub2(Un.m2, Ln.m2);
+      // d/dx: P = (xi, xi eta, xi zeta, xi eta zeta); nu modes (1, eta, zeta, eta zeta)
+      dir_q(mul2(k.kx, C0), mul2(k.kxt, C2), mul2(k.kxt, C4), mul2(k.kxtt, C6), u1, u3, u5, u7, Q3, Q5,
+            Q7, Q77, qx0, qx1, qx2, qx3);
+      // d/dy: P = (eta, xi eta, eta zeta, xi eta zeta); nu modes (1, xi, zeta, xi zeta)
+      dir_q(mul2(k.ky, C0), mul2(k.kyt, C1), mul2(k.kyt, C4), mul2(k.kytt, C5), u2, u3, u6, u7, Q3, Q6,
+            Q7, Q77, qy0, qy1, qy2, qy3);
+      // d/dz: P = (zeta, xi zeta, eta zeta, xi eta zeta); nu modes (1, xi, eta, xi eta)
+      dir_q(mul2(k.kz, C0), mul2(k.kzt, C1), mul2(k.kzt, C2), mul2(k.kztt, C3), u4, u5, u6, u7, Q5, Q6,
+            Q7, Q77, qz0, qz1, qz2, qz3);
+    } else {
+      // nu == 1: C0 = 8 (times the validity weight of the element), all other modes 0
+      const float2 dx = mul2(k.c0x, vw), dy = mul2(k.c0y, vw), dz = mul2(k.c0z, vw);
+      qx0 = mul2(dx, u1); qx1 = mul2(dx, Q3); qx2 = mul2(dx, Q5); qx3 = mul2(dx, Q77);
+      qy0 = mul2(dy, u2); qy1 = mul2(dy, Q3); qy2 = mul2(dy, Q6); qy3 = mul2(dy, Q77);
+      qz0 = mul2(dz, u4); qz1 = mul2(dz, Q5); qz2 = mul2(dz, Q6); qz3 = mul2(dz, Q77);
+    }
+    // half gradient per mode
+    const float2 q1 = qx0, q2 = qy0, q3 = add2(qx1, qy1), q4 = qz0, q5 = add2(qx2, qz1),
+                 q6 = add2(qy2, qz2), q7 = add2(qx3, add2(qy3, qz3));
+    float2 E, g0, g1, g2, g3, g4, g5, g6, g7;
+    if constexpr (HAS_F) {
+      const float2 u0 = add2(Lu.m0, Uu.m0);
+      // nb_m = -kf t^order(m) f_m
+      const float2 nb0 = mul2(k.nkf, add2(Lf.m0, Uf.m0));
+      const float2 nb1 = mul2(k.nkft, add2(Lf.m1, Uf.m1)), nb2 = mul2(k.nkft, add2(Lf.m2, Uf.m2)),
+                   nb4 = mul2(k.nkft, sub2(Uf.m0, Lf.m0));
+      const float2 nb3 = mul2(k.nkftt, add2(Lf.m3, Uf.m3)), nb5 = mul2(k.nkftt, sub2(Uf.m1, Lf.m1)),
+                   nb6 = mul2(k.nkftt, sub2(Uf.m2, Lf.m2));
+      const float2 nb7 = mul2(k.nkfttt, sub2(Uf.m3, Lf.m3));
+      const float2 t1 = add2(q1, nb1), t2 = add2(q2, nb2), t3 = add2(q3, nb3), t4 = add2(q4, nb4),
+                   t5 = add2(q5, nb5), t6 = add2(q6, nb6), t7 = add2(q7, nb7);
+      E = fma2(u0, nb0, fma2(u1, t1, fma2(u2, t2, fma2(u3, t3, fma2(u4, t4, fma2(u5, t5, fma2(u6, t6,
+               mul2(u7, t7))))))));
+      g0 = nb0; g1 = add2(q1, t1); g2 = add2(q2, t2); g3 = add2(q3, t3); g4 = add2(q4, t4);
+      g5 = add2(q5, t5); g6 = add2(q6, t6); g7 = add2(q7, t7);
+    } else {
+      E = fma2(u1, q1, fma2(u2, q2, fma2(u3, q3, fma2(u4, q4, fma2(u5, q5, fma2(u6, q6, mul2(u7, q7)))))));
+      g0 = f2(0.f); g1 = add2(q1, q1); g2 = add2(q2, q2); g3 = add2(q3, q3); g4 = add2(q4, q4);
+      g5 = add2(q5, q5); g6 = add2(q6, q6); g7 = add2(q7, q7);
+    }
+    // transposed z-stage
+    gLo.m0 = sub2(g0, g4); gLo.m1 = sub2(g1, g5); gLo.m2 = sub2(g2, g6); gLo.m3 = sub2(g3, g7);
+    gUp.m0 = add2(g0, g4); gUp.m1 = add2(g1, g5); gUp.m2 = add2(g2, g6); gUp.m3 = add2(g3, g7);
+    return E;
+  }
+};
+
+// Row-space gradient of one face: (sum, difference) coefficients of node rows a (upper y) and b.
+struct RowG {
+  float2 sa, da, sb, db;
+};
+__device__ __forceinline__ RowG face_to_rows(const Face& g) {   // transposed y-stage
+  RowG o;
+  o.sa = sub2(g.m0, g.m2); o.da = sub2(g.m1, g.m3);
+  o.sb = add2(g.m0, g.m2); o.db = add2(g.m1, g.m3);
+  return o;
+}
+
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK>
+__global__ void __launch_bounds__(DN_T3_MAXT, 1) k_fem3d_tma(const __grid_constant__ P3T p) {
+  using F = Fem3T<NM, VF, HAS_NU, HAS_F, NUMASK>;
+  constexpr int NF = F::NF;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_red[DN_T3_MAXT / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int nx = p.nx, LX = p.LX, S = p.S;
+  const int TYL = p.TY + 2;                              // node rows held per plane tile
+  const int NT = blockDim.x;                             // LX * (TY + 1)
+  const int fstride = TYL * nx, stage_floats = NF * fstride;
+  float* ring = reinterpret_cast<float*>(smem_raw);                                   // [S][NF][TYL][nx] (+16 B)
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats + 4);  // [S]
+  float* xbuf = reinterpret_cast<float*>(full + S);                                   // [2][4][NT]
+
+  // ---- work item: (b, z-chunk, y-tile)
+  int w_ = blockIdx.x;
+  const int ity = w_ % p.nty; w_ /= p.nty;
+  const int izc = w_ % p.nzc;
+  const int b = w_ / p.nzc;
+  const int ty0 = ity * p.TY, ty1 = min(p.ny, ty0 + p.TY);      // owned node rows [ty0, ty1)
+  const int jf = max(ty0 - 1, 0), jl = min(ty1, p.ny - 1);       // node rows loaded: jf..jl
+  const int nrl = jl - jf + 1, TR = jl - jf;                     // rows loaded, element rows
+  const int z0 = izc * p.ZC, z1 = min(p.nz, z0 + p.ZC);          // owned node planes [z0, z1)
+  const int zf = max(z0 - 1, 0), zl = min(z1, p.nz - 1);         // planes loaded: zf..zl
+  const int npl = zl - zf + 1;                                   // >= 2
+
+  // ---- producer: thread 0 copies one plane tile per stage: one bulk copy per field
+  int issued = 0, ist = 0;
+  auto issue_plane = [&]() {
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(nrl * nx * 4);
+      uint64_t* bar = full + ist;
+      float* dst = ring + ist * stage_floats;
+      mbar_arrive_expect_tx(bar, (uint32_t)NF * bytes);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        // rows of a plane are contiguous (stride_y == nx is an eligibility condition of this path)
+        const float* src = p.fld[f].p + (long long)b * p.fld[f].sb + (long long)(zf + issued) * p.fld[f].sz +
+                           (long long)jf * nx;
+        bulk_g2s(dst + f * fstride, src, bytes, bar);
+      }
+    }
+    ++issued;
+    ist = (ist + 1 == S) ? 0 : ist + 1;
+  };
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(full + s, 1);
+    fence_mbar_init();
+  }
+  pdl_wait();
+  {
+    const int n0 = min(S, npl);
+    for (int q = 0; q < n0; ++q) issue_plane();
+  }
+  __syncthreads();
+
+  // ---- thread geometry
+  const int r_raw = tid / LX, lx = tid - r_raw * LX;
+  const bool rvalid = r_raw < TR;
+  const int r = rvalid ? r_raw : 0;              // idle thread rows shadow row 0 (results dropped)
+  const int x0 = lx * 2;
+  const bool has_right = (x0 + 2) < nx;
+  const int er = jf + r;                         // element row == its upper node row (a); b = er + 1
+  const bool own_a = rvalid && (er >= ty0);      // node row a is stored by this thread; element row owned
+  const bool own_b = rvalid && (r == TR - 1) && (ty1 == p.ny);   // the domain's last node row
+  const float2 vw = f2(1.f, has_right ? 1.f : 0.f);
+  const K3& k = p.k3;
+  const float* sbase = ring + r * nx + x0;
+  float* gout = p.grad ? p.grad + (((long long)b * p.nz) * p.ny + er) * nx + x0 : nullptr;
+  const long long plane_elems = (long long)p.ny * nx;
+
+  Face Lu, Ln, Lf, Uu, Un, Uf;
+  float2 keepLa = f2(0.f), keepLb = f2(0.f), keepUa, keepUb;
+  RowG up;                                       // z-carry of the gradient (row space), upper plane
+  up.sa = up.da = up.sb = up.db = f2(0.f);
+  double acc = 0.0;
+  int st = 0;
+  uint32_t phase = 0;
+  int par = 0;
+
+  // publish the row-b partial sums and the right-neighbour shares of a finished plane
+  auto publish = [&](const RowG& d, float2& Na01, float& Nb2_out, float2& Nb01) {
+    const float2 loa = sub2(d.sa, d.da), hia = add2(d.sa, d.da);
+    const float2 lob = sub2(d.sb, d.db), hib = add2(d.sb, d.db);
+    Na01 = f2(loa.x, loa.y + hia.x);
+    Nb01 = f2(lob.x, lob.y + hib.x);
+    const float Na2 = hia.y, Nb2 = hib.y;
+    Nb2_out = Nb2;
+    float* xb = xbuf + par * 4 * NT;
+    *reinterpret_cast<float2*>(xb + 2 * tid) = Nb01;
+    xb[2 * NT + tid] = Nb2;
+    xb[3 * NT + tid] = Na2;
+  };
+  // after the barrier: gather the neighbours' shares for node row a (and b for the last row)
+  auto finalize = [&](float2 Na01, float2 Nb01, float2 keep_a, float2 keep_b, int zp, int bufpar) {
+    const float* xb = xbuf + bufpar * 4 * NT;
+    const bool zown = (zp >= z0) && (zp < z1);
+    if (own_a) {
+      float2 G = Na01;
+      if (r > 0) G = add2(G, *reinterpret_cast<const float2*>(xb + 2 * (tid - LX)));
+      if (lx > 0) {
+        G.x += xb[3 * NT + tid - 1];
+        if (r > 0) G.x += xb[2 * NT + tid - LX - 1];
+      }
+      G = mul2(G, keep_a);
+      if (zown) {
+        if (gout) *reinterpret_cast<float2*>(gout + (long long)zp * plane_elems) = G;
+        if (p.mode != 0) acc += (double)(G.x * G.x + G.y * G.y);
+      }
+    }
+    if (own_b) {
+      float2 G = Nb01;
+      if (lx > 0) G.x += xb[2 * NT + tid - 1];
+      G = mul2(G, keep_b);
+      if (zown) {
+        if (gout) *reinterpret_cast<float2*>(gout + (long long)zp * plane_elems + nx) = G;
+        if (p.mode != 0) acc += (double)(G.x * G.x + G.y * G.y);
+      }
+    }
+  };
+
+  // ---- first plane: nothing below it
+  {
+    mbar_wait(full + st, phase);
+    F::load_faces(p, sbase + st * stage_floats, nx, fstride, has_right, Lu, Ln, Lf, keepLa, keepLb);
+    __syncthreads();
+    if (issued < npl) issue_plane();
+    ++st;
+    if (st == S) { st = 0; phase ^= 1u; }
+  }
+  for (int s = zf; s < zl; ++s) {                // element layer s: planes s (lower) and s+1 (upper)
+    mbar_wait(full + st, phase);
+    F::load_faces(p, sbase + st * stage_floats, nx, fstride, has_right, Uu, Un, Uf, keepUa, keepUb);
+    Face gLo, gUp;
+    const float2 E = F::elem_pair(k, Lu, Uu, Ln, Un, Lf, Uf, vw, gLo, gUp);
+    if (p.mode == 0 && own_a && s >= z0 && s >= p.zloss_lo && s < p.zloss_hi) acc += (double)(E.x + E.y);
+    const RowG lo = face_to_rows(gLo);
+    RowG done;
+    done.sa = add2(up.sa, lo.sa); done.da = add2(up.da, lo.da);
+    done.sb = add2(up.sb, lo.sb); done.db = add2(up.db, lo.db);
+    up = face_to_rows(gUp);
+    float2 Na01, Nb01;
+    float Nb2;
+    publish(done, Na01, Nb2, Nb01);
+    __syncthreads();       // stage consumed by every thread; partial sums of plane s visible
+    if (issued < npl) issue_plane();
+    ++st;
+    if (st == S) { st = 0; phase ^= 1u; }
+    finalize(Na01, Nb01, keepLa, keepLb, s, par);
+    par ^= 1;
+    Lu = Uu; Ln = Un; Lf = Uf;
+    keepLa = keepUa; keepLb = keepUb;
+  }
+  // ---- top node plane of the domain: no element layer above it
+  if (z1 == p.nz) {
+    float2 Na01, Nb01;
+    float Nb2;
+    publish(up, Na01, Nb2, Nb01);
+    __syncthreads();
+    finalize(Na01, Nb01, keepLa, keepLb, p.nz - 1, par);
+  }
+
+  pdl_trigger();
+  acc = warp_sum(acc);
+  if (lane == 0) s_red[warp] = acc;
+  __syncthreads();
+  double cta = 0.0;
+  if (tid == 0)
+    for (int w = 0; w < nw; ++w) cta += s_red[w];
+  finish_loss_w0(p.red, cta);
+}
+
+// ---- dispatch (fem3d_tma_dispatch.cu) --------------------------------------------------------
+typedef cudaError_t (*launch3t_fn)(const P3T&, dim3, dim3, size_t, cudaStream_t);
+typedef int (*occ3t_fn)(int, size_t);
+launch3t_fn get_launch3t(int MK, int NU, int F, int NUMASK);
+occ3t_fn get_occ3t(int MK, int NU, int F, int NUMASK);
+
+template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+struct Kern3T {
+  static constexpr int NM = (MK == 4) ? 1 : MK;
+  static auto get() { return k_fem3d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK>; }
+};
+
+template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+cudaError_t prep3t() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(Kern3T<MK, HAS_NU, HAS_F, NUMASK>::get(),
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
+}
+
+template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+cudaError_t launch3t(const P3T& p, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+  cudaError_t e = prep3t<MK, HAS_NU, HAS_F, NUMASK>();
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  if (pdl_enabled()) { cfg.attrs = at; cfg.numAttrs = 1; }
+  return cudaLaunchKernelEx(&cfg, Kern3T<MK, HAS_NU, HAS_F, NUMASK>::get(), p);
+}
+
+template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+int occ3t(int threads, size_t smem) {
+  if (prep3t<MK, HAS_NU, HAS_F, NUMASK>() != cudaSuccess) return 0;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern3T<MK, HAS_NU, HAS_F, NUMASK>::get(), threads,
+                                                    smem) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+}  // namespace dn
