@@ -285,8 +285,10 @@ __global__ void __launch_bounds__(DN_T3_MAXT, 1) k_fem3d_tma(const __grid_consta
   float* gout = p.grad ? p.grad + (((long long)b * p.nz) * p.ny + er) * nx + x0 : nullptr;
   const long long plane_elems = (long long)p.ny * nx;
 
-  Face Lu, Ln, Lf, Uu, Un, Uf;
-  float2 keepLa = f2(0.f), keepLb = f2(0.f), keepUa, keepUb;
+  // node planes alternate between two register sets: the upper faces of one layer are the
+  // lower faces of the next (no copies)
+  struct Plane { Face u, n, f; float2 keep_a, keep_b; };
+  Plane PA, PB;
   RowG up;                                       // z-carry of the gradient (row space), upper plane
   up.sa = up.da = up.sb = up.db = f2(0.f);
   double acc = 0.0;
@@ -295,17 +297,15 @@ __global__ void __launch_bounds__(DN_T3_MAXT, 1) k_fem3d_tma(const __grid_consta
   int par = 0;
 
   // publish the row-b partial sums and the right-neighbour shares of a finished plane
-  auto publish = [&](const RowG& d, float2& Na01, float& Nb2_out, float2& Nb01) {
+  auto publish = [&](const RowG& d, float2& Na01, float2& Nb01) {
     const float2 loa = sub2(d.sa, d.da), hia = add2(d.sa, d.da);
     const float2 lob = sub2(d.sb, d.db), hib = add2(d.sb, d.db);
     Na01 = f2(loa.x, loa.y + hia.x);
     Nb01 = f2(lob.x, lob.y + hib.x);
-    const float Na2 = hia.y, Nb2 = hib.y;
-    Nb2_out = Nb2;
     float* xb = xbuf + par * 4 * NT;
     *reinterpret_cast<float2*>(xb + 2 * tid) = Nb01;
-    xb[2 * NT + tid] = Nb2;
-    xb[3 * NT + tid] = Na2;
+    xb[2 * NT + tid] = hib.y;
+    xb[3 * NT + tid] = hia.y;
   };
   // after the barrier: gather the neighbours' shares for node row a (and b for the last row)
   auto finalize = [&](float2 Na01, float2 Nb01, float2 keep_a, float2 keep_b, int zp, int bufpar) {
@@ -334,21 +334,24 @@ __global__ void __launch_bounds__(DN_T3_MAXT, 1) k_fem3d_tma(const __grid_consta
       }
     }
   };
-
-  // ---- first plane: nothing below it
-  {
-    mbar_wait(full + st, phase);
-    F::load_faces(p, sbase + st * stage_floats, nx, fstride, has_right, Lu, Ln, Lf, keepLa, keepLb);
-    __syncthreads();
+  auto next_stage = [&]() {
     if (issued < npl) issue_plane();
     ++st;
     if (st == S) { st = 0; phase ^= 1u; }
-  }
-  for (int s = zf; s < zl; ++s) {                // element layer s: planes s (lower) and s+1 (upper)
+  };
+
+  // ---- first plane: nothing below it
+  mbar_wait(full + st, phase);
+  F::load_faces(p, sbase + st * stage_floats, nx, fstride, has_right, PA.u, PA.n, PA.f, PA.keep_a, PA.keep_b);
+  __syncthreads();
+  next_stage();
+
+  // element layer s between plane s (L, registers) and plane s+1 (U, arriving)
+  auto layer = [&](Plane& L, Plane& U, int s) {
     mbar_wait(full + st, phase);
-    F::load_faces(p, sbase + st * stage_floats, nx, fstride, has_right, Uu, Un, Uf, keepUa, keepUb);
+    F::load_faces(p, sbase + st * stage_floats, nx, fstride, has_right, U.u, U.n, U.f, U.keep_a, U.keep_b);
     Face gLo, gUp;
-    const float2 E = F::elem_pair(k, Lu, Uu, Ln, Un, Lf, Uf, vw, gLo, gUp);
+    const float2 E = F::elem_pair(k, L.u, U.u, L.n, U.n, L.f, U.f, vw, gLo, gUp);
     if (p.mode == 0 && own_a && s >= z0 && s >= p.zloss_lo && s < p.zloss_hi) acc += (double)(E.x + E.y);
     const RowG lo = face_to_rows(gLo);
     RowG done;
@@ -356,24 +359,26 @@ __global__ void __launch_bounds__(DN_T3_MAXT, 1) k_fem3d_tma(const __grid_consta
     done.sb = add2(up.sb, lo.sb); done.db = add2(up.db, lo.db);
     up = face_to_rows(gUp);
     float2 Na01, Nb01;
-    float Nb2;
-    publish(done, Na01, Nb2, Nb01);
+    publish(done, Na01, Nb01);
     __syncthreads();       // stage consumed by every thread; partial sums of plane s visible
-    if (issued < npl) issue_plane();
-    ++st;
-    if (st == S) { st = 0; phase ^= 1u; }
-    finalize(Na01, Nb01, keepLa, keepLb, s, par);
+    next_stage();
+    finalize(Na01, Nb01, L.keep_a, L.keep_b, s, par);
     par ^= 1;
-    Lu = Uu; Ln = Un; Lf = Uf;
-    keepLa = keepUa; keepLb = keepUb;
+  };
+  int s = zf;
+  for (; s + 1 < zl; s += 2) {
+    layer(PA, PB, s);
+    layer(PB, PA, s + 1);
   }
+  const bool odd = s < zl;
+  if (odd) layer(PA, PB, s);
+
   // ---- top node plane of the domain: no element layer above it
   if (z1 == p.nz) {
     float2 Na01, Nb01;
-    float Nb2;
-    publish(up, Na01, Nb2, Nb01);
+    publish(up, Na01, Nb01);
     __syncthreads();
-    finalize(Na01, Nb01, keepLa, keepLb, p.nz - 1, par);
+    finalize(Na01, Nb01, odd ? PB.keep_a : PA.keep_a, odd ? PB.keep_b : PA.keep_b, p.nz - 1, par);
   }
 
   pdl_trigger();

@@ -45,62 +45,80 @@ static size_t smem_3t(int S, int nf, int TY, int nx, int threads) {
   return (size_t)S * nf * (TY + 2) * nx * 4 + 16 + (size_t)S * 8 + (size_t)2 * 4 * threads * 4;
 }
 
-// `occ` may be null (workspace sizing): then one CTA per SM is assumed.
+// Launch shape search.  Candidates: thread rows per tile (threads = rows * LX <= 512) x number of
+// z-chunks.  Cost model (the kernel is FP32-pipe bound, CTAs on one SM share the pipe):
+//   SM time ~ ceil(grid / SMs) * rows * (ZC + 1)   [thread-layers executed by the busiest SM]
+// with a penalty when fewer than 12 warps per SM are resident (latency hiding) and a preference
+// for a single wave.  `occ` may be null (workspace sizing): then the register bound is assumed.
 static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ) {
-  Plan3T pl;
-  memset(&pl, 0, sizeof(pl));
-  if (g->nx % 4 != 0 || g->nx < 8 || g->nx > 256) return pl;
-  pl.LX = g->nx / 2;
+  Plan3T best;
+  memset(&best, 0, sizeof(best));
+  if (g->nx % 4 != 0 || g->nx < 8 || g->nx > 256) return best;
+  const int LX = g->nx / 2;
   const int maxt = env_i3("DN_T3_THREADS", DN_T3_MAXT);
-  const int step = 32 / gcd_i(pl.LX, 32);               // thread rows come in multiples of this
-  int rows_max = (maxt / pl.LX) / step * step;           // element rows per tile (one thread row each)
-  if (rows_max < 2) return pl;
-  int TYmax = rows_max - 1;                              // owned node rows per tile (one halo element row)
-  TYmax = env_i3("DN_T3_TY", TYmax);
-  if (TYmax < 1) TYmax = 1;
-  if (TYmax > rows_max - 1) TYmax = rows_max - 1;
-  pl.nty = (g->ny + TYmax - 1) / TYmax;
-  pl.TY = (g->ny + pl.nty - 1) / pl.nty;
-  int rows = (pl.TY + 1 + step - 1) / step * step;
-  pl.threads = rows * pl.LX;
-  if (pl.threads > DN_T3_MAXT) return pl;
-  // the kernel indexes its exchange buffers by thread: TY is what the tile OWNS, rows what it runs
-  int S = env_i3("DN_T3_STAGES", 3);
-  if (S < 2) S = 2;
-  if (S > 8) S = 8;
-  while (S > 2 && smem_3t(S, nf, pl.TY, g->nx, pl.threads) > (size_t)kMaxDynSmem) --S;
-  pl.S = S;
-  pl.smem = smem_3t(S, nf, pl.TY, g->nx, pl.threads);
-  if (pl.smem > (size_t)kMaxDynSmem) return pl;
-  int cps = occ ? occ(pl.threads, pl.smem) : 1;
-  if (cps < 1) return pl;
-  // one wave: tiles * chunks <= resident slots; chunks of >= ZCmin planes
-  const long long tiles = (long long)g->batch * pl.nty;
-  const long long slots = (long long)sms * cps;
-  long long nzc = slots / tiles;
-  if (nzc < 1) nzc = 1;
-  int ZC = (int)((g->nz + nzc - 1) / nzc);
+  const int step = 32 / gcd_i(LX, 32);               // thread rows come in multiples of this
+  const int rows_cap = (maxt / LX) / step * step;
+  if (rows_cap < 2) return best;
+  const int ty_forced = env_i3("DN_T3_TY", 0), zc_forced = env_i3("DN_T3_ZC", 0);
   int zmin = env_i3("DN_T3_ZCMIN", 4);
   if (zmin < 1) zmin = 1;
-  if (ZC < zmin) ZC = zmin;
-  ZC = env_i3("DN_T3_ZC", ZC);
-  if (ZC < 1) ZC = 1;
-  if (ZC > g->nz) ZC = g->nz;
-  pl.ZC = ZC;
-  pl.nzc = (g->nz + ZC - 1) / ZC;
-  pl.grid = tiles * pl.nzc;
-  pl.ok = 1;
-  return pl;
+  int S0 = env_i3("DN_T3_STAGES", 3);
+  if (S0 < 2) S0 = 2;
+  if (S0 > 8) S0 = 8;
+  double best_cost = 0.0;
+  for (int rows = step; rows <= rows_cap; rows += step) {
+    if (rows < 2) continue;
+    int TYmax = rows - 1;
+    if (ty_forced > 0) { if (ty_forced > TYmax) continue; TYmax = ty_forced; }
+    const int nty = (g->ny + TYmax - 1) / TYmax;
+    const int TY = (g->ny + nty - 1) / nty;
+    if (ty_forced <= 0 && (TY + 1 + step - 1) / step * step != rows) continue;   // a smaller block covers it
+    const int threads = rows * LX;
+    int S = S0;
+    while (S > 2 && smem_3t(S, nf, TY, g->nx, threads) > (size_t)kMaxDynSmem) --S;
+    const size_t smem = smem_3t(S, nf, TY, g->nx, threads);
+    if (smem > (size_t)kMaxDynSmem) continue;
+    int cps = occ ? occ(threads, smem) : (int)(65536 / (threads * 128));
+    if (cps < 1) continue;
+    const long long tiles = (long long)g->batch * nty;
+    const int nzc_max = zc_forced > 0 ? 1 : (g->nz + zmin - 1) / zmin;
+    for (int nzc_try = 1; nzc_try <= nzc_max; ++nzc_try) {
+      int ZC = zc_forced > 0 ? zc_forced : (g->nz + nzc_try - 1) / nzc_try;
+      if (ZC > g->nz) ZC = g->nz;
+      if (ZC < 1) ZC = 1;
+      const int nzc = (g->nz + ZC - 1) / ZC;
+      if (zc_forced <= 0 && nzc != nzc_try) continue;
+      const long long grid = tiles * nzc;
+      const long long per_sm = (grid + sms - 1) / sms;               // CTAs the busiest SM runs
+      const long long resident = per_sm < cps ? per_sm : cps;
+      const double waves = (double)((per_sm + cps - 1) / cps);
+      const double warps = (double)resident * threads / 32.0;
+      double cost = (double)per_sm * rows * (ZC + 1);
+      if (warps < 12.0) cost *= 1.0 + 0.4 * (12.0 - warps) / 12.0;
+      cost *= 1.0 + 0.05 * (waves - 1.0);
+      if (!best.ok || cost < best_cost) {
+        best_cost = cost;
+        best.ok = 1; best.LX = LX; best.TY = TY; best.threads = threads; best.nty = nty;
+        best.ZC = ZC; best.nzc = nzc; best.S = S; best.grid = grid; best.smem = smem;
+      }
+      if (grid > 64LL * sms) break;                                   // finer chunks only add seams
+    }
+  }
+  return best;
 }
 
 long long plan3t_max_ctas(const dn_geom* g) {
   // workspace sizing: the default plan's grid, with head-room for the env knobs (a knob setting
   // that needs more is refused with DN_EWORKSPACE, never silently truncated)
-  Plan3T pl = plan3t(g, DN_T2_MAXF, 148, nullptr);
-  if (!pl.ok) return 0;
-  const long long tiles = (long long)g->batch * pl.nty;
-  const long long zc4 = (g->nz + 3) / 4;
-  return 4 * tiles * zc4;
+  if (g->nx % 4 != 0 || g->nx < 8 || g->nx > 256) return 0;
+  // the finest shape the planner may pick: tiles owning one node row... bounded in practice by
+  // one thread-row step and chunks of DN_T3_ZCMIN (>= 1, default 4) planes
+  const int LX = g->nx / 2;
+  const int step = 32 / gcd_i(LX, 32);
+  const int ty_min = step > 1 ? step - 1 : 1;
+  const long long nty = (g->ny + ty_min - 1) / ty_min;
+  const long long nzc = (g->nz + 3) / 4;
+  return (long long)g->batch * nty * nzc;
 }
 
 int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, const Field& numask,
