@@ -39,8 +39,20 @@ WORKLOADS = {
     "poisson3d_param_64_b16": (3, 64, 16, 20, "Poisson 3D parametric 64^3 Q1 hex, batch 16/GPU (u, source, sink, f)"),
     "poisson3d_128_b1": (3, 128, 1, 24, "Poisson 3D 128^3, variable nu, f, two masks (roofline point)"),
     "poisson3d_256_b1": (3, 256, 1, 20, "Poisson 3D non-parametric 256^3 (u, nu, bc1, f)"),
+    # one 256^3 field split into z-slabs over the ranks (strong scaling; halo exchange + loss all-reduce)
+    "poisson3d_256_slab": (3, 256, 1, 20, "Poisson 3D non-parametric 256^3, z-slabs over all ranks, 1-plane halo exchange"),
 }
 DEFAULT = "poisson2d_param_256_b64"
+
+
+def measured_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed ncu capture of this workload (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(name)
+    except Exception:   # noqa: BLE001
+        return None
 
 
 def measured_peak_gbs():
@@ -354,6 +366,12 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = dof_step * world * Ke / float(te.item()) / 1e9
     clocks = sampler.stop() if rank == 0 else None
+    train = None
+    if args.train_steps > 0 and name in ("poisson2d_param_256_b64", "poisson3d_param_64_b16"):
+        try:
+            train = train_step_rate(name, dev, world, rank, args.train_steps, 5)
+        except Exception as e:   # noqa: BLE001  (the FEM line must still be printed)
+            train = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -375,15 +393,151 @@ def run_ours(args):
                        "timing": f"CUDA events around {K} steps, median of {reps} repetitions, max over ranks",
                        "parallelism": f"dp{world} (batch sharded, no data-path collective)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_dof": bpd, "kernel": "k_fem2d" if nsd == 2 else "k_fem3d"},
+                         "frac": achieved / peak, "traffic": (measured_traffic(name) or {}).get("bytes"),
+                         "traffic_source": (measured_traffic(name) or {}).get("source"),
+                         "peak_source": peak_src, "bytes_per_dof": bpd,
+                         "algorithmic_bytes_per_launch": step_bytes,
+                         "kernel": "k_fem2d_tma" if nsd == 2 else "k_fem3d_tma"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": Ke, "note": "pinned host -> device copy of all input fields + fused launch + loss.item()"},
             "gpu_launches": K,
             "clocks": clocks,
+            "train": train,
         }
         print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ train step
+def train_step_rate(name, dev, world, rank, steps, warmup):
+    """Full training step of the parametric config: UNet forward + fused FEM loss + backward +
+    DDP gradient all-reduce (NCCL) + Adam; batch per GPU fixed (weak scaling); synthetic inputs
+    resident on the device; CUDA events around `steps` steps, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from diffnet_b200.networks import UNet
+    from diffnet_b200.poisson import PoissonIBN3D, PoissonParametric2D
+    from diffnet_b200.synthetic import poisson2d_parametric_batch, poisson3d_parametric_batch
+    nsd, size, B, _, _ = WORKLOADS[name]
+    torch.manual_seed(0)
+    if nsd == 2:
+        net = UNet(3, 1).to(dev)
+        mod = PoissonParametric2D(net, domain_size=size, batch_size=B, learning_rate=3e-4)
+        _, inputs, f = poisson2d_parametric_batch(B, size, dev, seed=4321 + rank)
+        batch = (inputs, f)
+    else:
+        net = UNet(1, 1, nd=3).to(dev)
+        mod = PoissonIBN3D(net, domain_size=size, batch_size=B, learning_rate=3e-4)
+        _, src, sink, f = poisson3d_parametric_batch(B, size, dev, seed=4321 + rank)
+        batch = (src, sink, f)
+    mod.to(dev)
+    nparams = sum(p.numel() for p in net.parameters())
+    if world > 1:
+        mod.network = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index],
+                                                               gradient_as_bucket_view=True)
+    opt = mod.configure_optimizers()[0][0]
+    mod.train()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = mod.training_step(batch, 0)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"steps_per_s": 1e3 / ms, "samples_per_s": 1e3 / ms * B * world, "ms_per_step": ms, "steps": steps,
+            "batch_per_gpu": B, "network": f"UNet nd={nsd} ({nparams} params)", "loss": float(loss),
+            "note": "UNet fwd + fused FEM loss + bwd + DDP all-reduce (NCCL) + Adam; fp32; weak scaling"}
+
+
+# ------------------------------------------------------------------------------------ z-slab arm
+def run_slab(args):
+    """One 256^3 field over all ranks: per step = halo exchange of u (NCCL
+    send/recv) + fused kernel on the slab + scalar loss all-reduce.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from diffnet_b200 import ops
+    from diffnet_b200.slab import ZSlabPoisson3D, make_slab
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    name = args.workload
+    nsd, N, _, bpd, desc = WORKLOADS[name]
+    h = 1.0 / (N - 1)
+    geom = ops.Geometry(3, N, N, N, h, h, h, 2)
+    sp = ZSlabPoisson3D(geom)
+    sl = make_slab(N, world, rank)
+    nl = sl.hi - sl.lo
+    g = torch.Generator(device=dev).manual_seed(1234 + sl.lo)
+    # synthetic slab-local fields (solve_in_object_3d.py:37-62 shapes: nu = object mask, bc1 = outside, f = 500)
+    zz = torch.arange(sl.lo, sl.hi, device=dev).float()[:, None, None] / (N - 1) - 0.5
+    yy = torch.arange(N, device=dev).float()[None, :, None] / (N - 1) - 0.5
+    xx = torch.arange(N, device=dev).float()[None, None, :] / (N - 1) - 0.5
+    inside = ((xx ** 2 + yy ** 2 + zz ** 2) < 0.16).float()
+    nsets = 2
+    us = [torch.randn(nl, N, N, device=dev, generator=g) for _ in range(nsets)]
+    sp.set_fields(nu=inside, f=torch.full_like(inside, 500.0), dirichlet=[(1.0 - inside, 0.0)],
+                  already_local=True, c_k=0.5)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def step(i):
+        return sp.loss_and_grad(us[i % nsets], zero_halo_grad=False)
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        loss, grad = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    dof = N ** 3
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        value = dof / (ms * 1e-3) / 1e9
+        achieved = dof * bpd / (ms * 1e-3) / 1e9 / world
+        print(json.dumps({
+            "metric": "FEM loss+grad throughput", "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "desc": desc, "grid": [N, N, N], "slab_planes_rank0": nl,
+                       "launch": "eager", "l2": f"slab working set {nl * N * N * bpd / 1e6:.0f} MB per rank",
+                       "timing": f"CUDA events around {K} steps, max over ranks",
+                       "parallelism": f"z-slab x{world}: ncclSend/Recv of 2 halo planes + loss all-reduce per step"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_dof": bpd, "kernel": "k_fem3d_tma",
+                         "note": "per-GPU: algorithmic bytes of the rank's owned planes / step time"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": None, "loss": float(loss)}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -398,9 +552,15 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=20,
+                    help="also time this many full training steps (UNet + loss + DDP + Adam); 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "poisson3d_256_slab":
+            args.workload = "poisson3d_256_b1"
         run_reference(args)
+    elif args.workload == "poisson3d_256_slab":
+        run_slab(args)
     else:
         run_ours(args)
 

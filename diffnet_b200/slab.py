@@ -1,0 +1,176 @@
+"""z-slab domain decomposition of ONE large 3-D field over the ranks of a process group
+(non-parametric case; new functionality -- the reference runs 128^3 on one GPU,
+IBN/poisson-3d/non-parametric/solve_in_object_3d.py).
+
+Rank k owns node planes [z0_k, z1_k) and stores planes [z0_k - 1, z1_k + 1) clipped to the
+domain: a one-plane halo on each side.  Static fields (nu, f, masks) are cut once with their
+halos.  Every step:
+  1. halo exchange of u: each rank sends its first / last OWNED plane to the rank below / above
+     (2 planes x ny x nx x 4 B -- 256 KB at 256^2) with batched point-to-point ops (NCCL send/recv
+     over NVLink on GPUs, gloo on CPU);
+  2. the fused kernel runs on the local slab: the energy is summed over element layers whose
+     lower plane is owned (``z_own``), divided by the GLOBAL element count (``mean_count``); the
+     gradient of the owned planes is complete without a reverse exchange because the kernel
+     evaluates the halo element layers too;
+  3. one scalar all-reduce(SUM) of the loss partials (only the value: gradients are local);
+  4. the optimiser (Adam on u, solve_in_object_3d.py:123) updates the owned planes locally.
+
+The compute backend is a callable ``energy(geom, u, z_own=, mean_count=, **fields) -> (loss, grad)``;
+the product default is the CUDA op.  The CPU tests (gloo, world_size 2) inject the oracle there to
+check the partitioning, the exchange and the global normalisation without a GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def slab_bounds(nz: int, world: int, rank: int) -> tuple[int, int]:
+    """Owned node planes [z0, z1) of `rank`: contiguous, sizes differing by at most one."""
+    base, rem = divmod(nz, world)
+    z0 = rank * base + min(rank, rem)
+    return z0, z0 + base + (1 if rank < rem else 0)
+
+
+@dataclass
+class Slab:
+    rank: int
+    world: int
+    nz: int                 # global node planes
+    z0: int                 # owned [z0, z1)
+    z1: int
+    lo: int                 # stored [lo, hi) = owned + halos, clipped
+    hi: int
+
+    @property
+    def own_local(self) -> tuple[int, int]:
+        return self.z0 - self.lo, self.z1 - self.lo
+
+    @property
+    def has_below(self) -> bool:
+        return self.z0 > 0
+
+    @property
+    def has_above(self) -> bool:
+        return self.z1 < self.nz
+
+
+def make_slab(nz: int, world: int, rank: int) -> Slab:
+    z0, z1 = slab_bounds(nz, world, rank)
+    if z1 - z0 < 1:
+        raise ValueError(f"rank {rank} owns no plane: nz={nz} < world={world}")
+    return Slab(rank, world, nz, z0, z1, max(z0 - 1, 0), min(z1 + 1, nz))
+
+
+def cut(t: torch.Tensor, slab: Slab, zdim: int = -3) -> torch.Tensor:
+    """The stored planes [lo, hi) of a global field (a copy: each rank keeps only its slab)."""
+    return t.narrow(zdim, slab.lo, slab.hi - slab.lo).contiguous()
+
+
+def _default_energy(geom, u, **kw):
+    loss, grad, _ = ops.energy_raw(geom, u, **kw)
+    return loss, grad
+
+
+class ZSlabPoisson3D:
+    """Loss + gradient of the Poisson energy of one (nz, ny, nx) field split into z-slabs.
+
+    ``u_local`` is this rank's (hi-lo, ny, nx) slab INCLUDING halos; only the owned planes are
+    optimisation variables, the halos are refreshed from the neighbours at every step."""
+
+    def __init__(self, geom_global: ops.Geometry, group=None, energy: Optional[Callable] = None):
+        if geom_global.nsd != 3:
+            raise ValueError("z-slab decomposition is for 3-D meshes")
+        self.g = geom_global
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.slab = make_slab(geom_global.nz, self.world, self.rank)
+        nl = self.slab.hi - self.slab.lo
+        self.geom_local = ops.Geometry(3, geom_global.nx, geom_global.ny, nl, geom_global.hx, geom_global.hy,
+                                       geom_global.hz, geom_global.ngp_1d)
+        self.energy = energy or _default_energy
+        self.fields = {}
+        self.dirichlet: Sequence = ()
+        self.consts = {}
+
+    # ---------------------------------------------------------------- setup
+    def set_fields(self, nu=None, f=None, dirichlet=(), already_local=False, **consts):
+        """Static fields: global tensors (cut here, halos included) or, with ``already_local``,
+        this rank's slabs.  ``consts`` = c_k, c_f, scale."""
+        c = (lambda t: t) if already_local else (lambda t: cut(t, self.slab))
+        self.fields = {k: c(v) for k, v in (("nu", nu), ("f", f)) if v is not None}
+        self.dirichlet = [(c(m), (c(v) if torch.is_tensor(v) else v)) for m, v in dirichlet]
+        self.consts = consts
+
+    def local_of(self, u_global: torch.Tensor) -> torch.Tensor:
+        return cut(u_global, self.slab)
+
+    # ---------------------------------------------------------------- per step
+    def exchange_halos(self, u_local: torch.Tensor) -> None:
+        """In place: halo planes of `u_local` <- the neighbours' boundary owned planes.  Planes of a
+        contiguous (nl, ny, nx) slab are contiguous, so they are sent and received in place (no
+        staging copies); the four point-to-point ops go out as one NCCL group."""
+        if self.world == 1:
+            return
+        if not u_local.is_contiguous():
+            raise ValueError("u_local must be contiguous (planes are exchanged in place)")
+        s = self.slab
+        o0, o1 = s.own_local
+        u = u_local.detach()
+        opsl = []
+        if s.has_below:     # my first owned plane -> rank-1's upper halo; its last owned -> my lower halo
+            opsl += [dist.P2POp(dist.isend, u[o0], self._peer(-1), self.group),
+                     dist.P2POp(dist.irecv, u[0], self._peer(-1), self.group)]
+        if s.has_above:
+            opsl += [dist.P2POp(dist.isend, u[o1 - 1], self._peer(+1), self.group),
+                     dist.P2POp(dist.irecv, u[u.shape[0] - 1], self._peer(+1), self.group)]
+        for w in dist.batch_isend_irecv(opsl):
+            w.wait()
+
+    def _peer(self, d: int) -> int:
+        r = self.rank + d
+        return dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def loss_and_grad(self, u_local: torch.Tensor, exchange: bool = True, zero_halo_grad: bool = True,
+                      reduce_loss: bool = True):
+        """(loss, d loss / d u on this rank's slab).  With ``reduce_loss`` the loss is the GLOBAL
+        value (one scalar all-reduce), identical on every rank; otherwise this rank's partial.
+        The gradient is complete on the owned planes; the halo planes are zeroed unless
+        ``zero_halo_grad=False`` (their values are then partial sums nobody should use)."""
+        if exchange:
+            self.exchange_halos(u_local)
+        g = self.g
+        count = float((g.nx - 1) * (g.ny - 1) * (g.nz - 1))
+        loss, grad = self.energy(self.geom_local, u_local, z_own=self.slab.own_local, mean_count=count,
+                                 dirichlet=self.dirichlet, **self.fields, **self.consts)
+        grad = grad.reshape(u_local.shape)
+        o0, o1 = self.slab.own_local
+        if zero_halo_grad:
+            if o0 > 0:
+                grad[:o0].zero_()
+            if o1 < grad.shape[0]:
+                grad[o1:].zero_()
+        if reduce_loss and self.world > 1:
+            loss = loss.clone()
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        return loss, grad
+
+    def gather_owned(self, u_local: torch.Tensor) -> torch.Tensor:
+        """All ranks' owned planes concatenated in z (for checks / output)."""
+        o0, o1 = self.slab.own_local
+        mine = u_local[o0:o1].contiguous()
+        if self.world == 1:
+            return mine
+        sizes = [slab_bounds(self.g.nz, self.world, r) for r in range(self.world)]
+        most = max(b - a for a, b in sizes)          # all_gather wants equal shapes: pad to the largest slab
+        pad = torch.zeros((most,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        pad[:mine.shape[0]] = mine
+        bufs = [torch.empty_like(pad) for _ in sizes]
+        dist.all_gather(bufs, pad, group=self.group)
+        return torch.cat([b[:hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)

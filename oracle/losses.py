@@ -42,10 +42,11 @@ def _dirichlet(u, dirichlet):
     return u
 
 
-def energy_loss(fem: Q1Oracle, u, nu=None, f=None, f_gp=None, dirichlet=(),
-                nu_zero_mask=None, c_k=1.0, c_f=1.0, scale=1.0, reduction="mean"):
-    """scale * gpw_g * (c_k * nu_g * |grad u|_g^2 - c_f * u_g * f_g), summed over
-    Gauss points, then mean (or sum) over batch x elements.  SURVEY.md App. A.4."""
+def energy_density(fem: Q1Oracle, u, nu=None, f=None, f_gp=None, dirichlet=(),
+                   nu_zero_mask=None, c_k=1.0, c_f=1.0, scale=1.0):
+    """Per-element energy (B, *elems): scale * sum_g gpw_g * (c_k * nu_g * |grad u|_g^2 -
+    c_f * u_g * f_g) -- ``res_elmwise`` after ``torch.sum(res_elmwise, 1)`` in every reference
+    loss() (e.g. 0_base.py:51-54)."""
     u = _dirichlet(u, dirichlet)
     if nu is not None and nu_zero_mask is not None:      # e2_..._neumann.py:44
         nu = torch.where(nu_zero_mask > 0.5, nu * 0.0, nu)
@@ -60,7 +61,14 @@ def energy_loss(fem: Q1Oracle, u, nu=None, f=None, f_gp=None, dirichlet=(),
     if f_gp is not None and c_f != 0.0:
         integrand = integrand - c_f * (u_gp * f_gp)
     res = scale * _gpw_b(fem, u_gp) * integrand
-    res = torch.sum(res, 1)
+    return torch.sum(res, 1)
+
+
+def energy_loss(fem: Q1Oracle, u, nu=None, f=None, f_gp=None, dirichlet=(),
+                nu_zero_mask=None, c_k=1.0, c_f=1.0, scale=1.0, reduction="mean"):
+    """scale * gpw_g * (c_k * nu_g * |grad u|_g^2 - c_f * u_g * f_g), summed over
+    Gauss points, then mean (or sum) over batch x elements.  SURVEY.md App. A.4."""
+    res = energy_density(fem, u, nu, f, f_gp, dirichlet, nu_zero_mask, c_k, c_f, scale)
     return torch.mean(res) if reduction == "mean" else torch.sum(res)
 
 
