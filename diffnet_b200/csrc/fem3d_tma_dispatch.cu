@@ -1,5 +1,6 @@
 // Launch planning and runtime -> compile-time dispatch of the streaming 3-D kernel family
 // (instantiated in gen/fem3dt_mk*.cu).
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -37,88 +38,146 @@ static int env_i3(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
-
-struct Plan3T { int ok, LX, TY, threads, nty, ZC, nzc, S; long long grid; size_t smem; };
-
-static size_t smem_3t(int S, int nf, int TY, int nx, int threads) {
-  return (size_t)S * nf * (TY + 2) * nx * 4 + 16 + (size_t)S * 8 + (size_t)2 * 4 * threads * 4;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_fn get_encode() {
+  static encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_fn)ptr;
+    else
+      cudaGetLastError();
+  }
+  return fn;
 }
 
-// Launch shape search.  Candidates: thread rows per tile (threads = rows * LX <= 512) x number of
-// z-chunks.  Cost model (the kernel is FP32-pipe bound, CTAs on one SM share the pipe):
-//   SM time ~ ceil(grid / SMs) * rows * (ZC + 1)   [thread-layers executed by the busiest SM]
-// with a penalty when fewer than 12 warps per SM are resident (latency hiding) and a preference
-// for a single wave.  `occ` may be null (workspace sizing): then the register bound is assumed.
+// 4-D map (x, y, z, b) over one strided fp32 field; box = BX x BY x 1 x 1, zero fill outside
+static bool make_map(CUtensorMap* tm, const Field& f, const dn_geom* g, int BX, int BY, int* bmul) {
+  encode_fn enc = get_encode();
+  if (!enc) return false;
+  const bool bc = (f.sb == 0) || (g->batch == 1);
+  *bmul = bc ? 0 : 1;
+  cuuint64_t dims[4] = {(cuuint64_t)g->nx, (cuuint64_t)g->ny, (cuuint64_t)g->nz, (cuuint64_t)(bc ? 1 : g->batch)};
+  const cuuint64_t plane = (cuuint64_t)g->ny * g->nx * 4, vol = plane * (cuuint64_t)g->nz;
+  cuuint64_t strides[3] = {(cuuint64_t)f.sy * 4, g->nz > 1 ? (cuuint64_t)f.sz * 4 : plane,
+                           bc ? vol : (cuuint64_t)f.sb * 4};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] == 0 || strides[i] % 16) return false;
+  cuuint32_t box[4] = {(cuuint32_t)BX, (cuuint32_t)BY, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)f.p, dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Plan3T {
+  int ok, LXT, LXo, hl, ntx, rows, TY, nty, threads, ZC, nzc, S, BX, BY, fstride;
+  long long grid;
+  size_t smem;
+};
+
+static size_t smem_3t(int S, int nf, int fstride, int threads) {
+  return (size_t)S * nf * fstride * 4 + (size_t)S * 8 + (size_t)2 * 4 * threads * 4 + 64;
+}
+
+// Launch shape search.  Candidates: x-tile width (owned element pairs per tile row) x thread rows
+// per tile (threads = LXT * rows <= 512) x number of z-chunks.  Cost model (the kernel is FP32-pipe
+// bound; CTAs on one SM share the pipe):
+//   SM time ~ ceil(grid / SMs) * threads * (ZC + 1)   [thread-layers executed by the busiest SM]
+// with a penalty when fewer than 12 warps per SM are resident and a mild preference for one wave.
+// `occ` may be null (workspace sizing): then the register bound is assumed.
 static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ) {
   Plan3T best;
   memset(&best, 0, sizeof(best));
-  if (g->nx % 4 != 0 || g->nx < 8 || g->nx > 256) return best;
-  const int LX = g->nx / 2;
+  if (g->nx % 4 != 0 || g->nx < 8) return best;
+  const int npairs = g->nx / 2;
   const int maxt = env_i3("DN_T3_THREADS", DN_T3_MAXT);
-  const int step = 32 / gcd_i(LX, 32);               // thread rows come in multiples of this
-  const int rows_cap = (maxt / LX) / step * step;
-  if (rows_cap < 2) return best;
-  const int ty_forced = env_i3("DN_T3_TY", 0), zc_forced = env_i3("DN_T3_ZC", 0);
+  const int lx_forced = env_i3("DN_T3_LX", 0), ty_forced = env_i3("DN_T3_TY", 0), zc_forced = env_i3("DN_T3_ZC", 0);
   int zmin = env_i3("DN_T3_ZCMIN", 4);
   if (zmin < 1) zmin = 1;
   int S0 = env_i3("DN_T3_STAGES", 3);
   if (S0 < 2) S0 = 2;
   if (S0 > 8) S0 = 8;
   double best_cost = 0.0;
-  for (int rows = step; rows <= rows_cap; rows += step) {
-    if (rows < 2) continue;
-    int TYmax = rows - 1;
-    if (ty_forced > 0) { if (ty_forced > TYmax) continue; TYmax = ty_forced; }
-    const int nty = (g->ny + TYmax - 1) / TYmax;
-    const int TY = (g->ny + nty - 1) / nty;
-    if (ty_forced <= 0 && (TY + 1 + step - 1) / step * step != rows) continue;   // a smaller block covers it
-    const int threads = rows * LX;
-    int S = S0;
-    while (S > 2 && smem_3t(S, nf, TY, g->nx, threads) > (size_t)kMaxDynSmem) --S;
-    const size_t smem = smem_3t(S, nf, TY, g->nx, threads);
-    if (smem > (size_t)kMaxDynSmem) continue;
-    int cps = occ ? occ(threads, smem) : (int)(65536 / (threads * 128));
-    if (cps < 1) continue;
-    const long long tiles = (long long)g->batch * nty;
-    const int nzc_max = zc_forced > 0 ? 1 : (g->nz + zmin - 1) / zmin;
-    for (int nzc_try = 1; nzc_try <= nzc_max; ++nzc_try) {
-      int ZC = zc_forced > 0 ? zc_forced : (g->nz + nzc_try - 1) / nzc_try;
-      if (ZC > g->nz) ZC = g->nz;
-      if (ZC < 1) ZC = 1;
-      const int nzc = (g->nz + ZC - 1) / ZC;
-      if (zc_forced <= 0 && nzc != nzc_try) continue;
-      const long long grid = tiles * nzc;
-      const long long per_sm = (grid + sms - 1) / sms;               // CTAs the busiest SM runs
-      const long long resident = per_sm < cps ? per_sm : cps;
-      const double waves = (double)((per_sm + cps - 1) / cps);
-      const double warps = (double)resident * threads / 32.0;
-      double cost = (double)per_sm * rows * (ZC + 1);
-      if (warps < 12.0) cost *= 1.0 + 0.4 * (12.0 - warps) / 12.0;
-      cost *= 1.0 + 0.05 * (waves - 1.0);
-      if (!best.ok || cost < best_cost) {
-        best_cost = cost;
-        best.ok = 1; best.LX = LX; best.TY = TY; best.threads = threads; best.nty = nty;
-        best.ZC = ZC; best.nzc = nzc; best.S = S; best.grid = grid; best.smem = smem;
+  const int cand[5] = {npairs, 16, 32, 64, 128};
+  for (int ci = 0; ci < 5; ++ci) {
+    int LXo = cand[ci];
+    if (lx_forced > 0) { if (ci > 0) break; LXo = lx_forced; }
+    if (LXo > npairs) LXo = npairs;
+    if (ci > 0 && LXo >= npairs) continue;             // same as the full-width candidate
+    const int ntx = (npairs + LXo - 1) / LXo;
+    const int hl = ntx > 1 ? 1 : 0;
+    const int LXT = LXo + hl;
+    if (LXT * 2 > maxt) continue;
+    const int BX = (2 * LXT + 2 + 2 * hl + 3) / 4 * 4;   // + alignment slack when the tile starts at an odd pair
+    if (BX > 256) continue;
+    for (int rows = 2; rows * LXT <= maxt; ++rows) {
+      int TYmax = rows - 1;
+      if (ty_forced > 0) { if (ty_forced > TYmax) continue; TYmax = ty_forced; }
+      const int nty = (g->ny + TYmax - 1) / TYmax;
+      const int TY = (g->ny + nty - 1) / nty;
+      // element rows a tile runs: TY+1 with a halo row above (interior tiles), fewer at the domain edges
+      int need = nty >= 3 ? TY + 1 : (nty == 2 ? TY : TY - 1);
+      if (need < 1) need = 1;
+      if (ty_forced <= 0 && rows != need && !(need < 2 && rows == 2)) continue;   // a smaller block covers it
+      if (rows < need) continue;
+      const int BY = TY + 2;
+      if (BY > 256) continue;
+      const int threads = (rows * LXT + 31) / 32 * 32;
+      if (threads > DN_T3_MAXT) continue;
+      const int fstride = (BX * BY + 31) / 32 * 32;
+      int S = S0;
+      while (S > 2 && smem_3t(S, nf, fstride, threads) > (size_t)kMaxDynSmem) --S;
+      const size_t smem = smem_3t(S, nf, fstride, threads);
+      if (smem > (size_t)kMaxDynSmem) continue;
+      int cps = occ ? occ(threads, smem) : (int)(65536 / (threads * 128));
+      if (cps < 1) continue;
+      const long long tiles = (long long)g->batch * nty * ntx;
+      const int nzc_max = zc_forced > 0 ? 1 : (g->nz + zmin - 1) / zmin;
+      for (int nzc_try = 1; nzc_try <= nzc_max; ++nzc_try) {
+        int ZC = zc_forced > 0 ? zc_forced : (g->nz + nzc_try - 1) / nzc_try;
+        if (ZC > g->nz) ZC = g->nz;
+        if (ZC < 1) ZC = 1;
+        const int nzc = (g->nz + ZC - 1) / ZC;
+        if (zc_forced <= 0 && nzc != nzc_try) continue;
+        const long long grid = tiles * nzc;
+        const long long per_sm = (grid + sms - 1) / sms;             // CTAs the busiest SM runs
+        const long long resident = per_sm < cps ? per_sm : cps;
+        const double waves = (double)((per_sm + cps - 1) / cps);
+        const double warps = (double)resident * threads / 32.0;
+        double cost = (double)per_sm * threads * (ZC + 1);
+        if (warps < 12.0) cost *= 1.0 + 0.4 * (12.0 - warps) / 12.0;
+        if (LXT % 32) cost *= 1.2;      // warps straddling tile rows: measured 15-20 % slower per thread-layer
+        cost *= 1.0 + 0.05 * (waves - 1.0);
+        if (!best.ok || cost < best_cost) {
+          best_cost = cost;
+          best.ok = 1; best.LXT = LXT; best.LXo = LXo; best.hl = hl; best.ntx = ntx; best.rows = rows;
+          best.TY = TY; best.nty = nty; best.threads = threads; best.ZC = ZC; best.nzc = nzc; best.S = S;
+          best.BX = BX; best.BY = BY; best.fstride = fstride; best.grid = grid; best.smem = smem;
+        }
+        if (grid > 64LL * sms) break;                                 // finer chunks only add seams
       }
-      if (grid > 64LL * sms) break;                                   // finer chunks only add seams
     }
   }
   return best;
 }
 
 long long plan3t_max_ctas(const dn_geom* g) {
-  // workspace sizing: the default plan's grid, with head-room for the env knobs (a knob setting
-  // that needs more is refused with DN_EWORKSPACE, never silently truncated)
-  if (g->nx % 4 != 0 || g->nx < 8 || g->nx > 256) return 0;
-  // the finest shape the planner may pick: tiles owning one node row... bounded in practice by
-  // one thread-row step and chunks of DN_T3_ZCMIN (>= 1, default 4) planes
-  const int LX = g->nx / 2;
-  const int step = 32 / gcd_i(LX, 32);
-  const int ty_min = step > 1 ? step - 1 : 1;
-  const long long nty = (g->ny + ty_min - 1) / ty_min;
-  const long long nzc = (g->nz + 3) / 4;
-  return (long long)g->batch * nty * nzc;
+  if (g->nx % 4 != 0 || g->nx < 8) return 0;
+  // workspace sizing: an upper bound on what the planner may pick -- x tiles of >= 16 pairs,
+  // y tiles owning >= 1 row when forced by env (default search: >= 1), chunks of >= 4 planes by
+  // default.  Bounded to keep the workspace small; a knob setting that needs more is refused.
+  const long long ntx = (g->nx / 2 + 15) / 16, nty = (g->ny + 1) / 2, nzc = (g->nz + 3) / 4;
+  long long n = (long long)g->batch * ntx * nty * nzc;
+  const long long cap = 1LL << 22;
+  return n < cap ? n : cap;
 }
 
 int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, const Field& numask,
@@ -132,27 +191,31 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   const int NU = nu.p ? 1 : 0, F = f.p ? 1 : 0, NMK = numask.p ? 1 : 0;
   launch3t_fn fn = get_launch3t(MK, NU, F, NMK);
   occ3t_fn occ = get_occ3t(MK, NU, F, NMK);
-  if (!fn || !occ) return DN_OK;
+  if (!fn || !occ || !get_encode()) return DN_OK;
+  Field fl[DN_T2_MAXF];
   P3T p;
   memset(&p, 0, sizeof(p));
   int nf = 0;
-  p.fld[nf++] = u;
-  if (NU) p.fld[nf++] = nu;
-  if (F) p.fld[nf++] = f;
-  if (NMK) p.fld[nf++] = numask;
-  for (int i = 0; i < nmasks; ++i) { p.fld[nf++] = mk[i].m; p.mval[i] = mk[i].v; }
-  if (MK == 4) p.fld[nf++] = mk[0].vf;
-  for (int i = 0; i < nf; ++i)
-    if (p.fld[i].sy != g->nx) return DN_OK;      // bulk copies take whole runs of rows
+  fl[nf++] = u;
+  if (NU) fl[nf++] = nu;
+  if (F) fl[nf++] = f;
+  if (NMK) fl[nf++] = numask;
+  for (int i = 0; i < nmasks; ++i) { fl[nf++] = mk[i].m; p.mval[i] = mk[i].v; }
+  if (MK == 4) fl[nf++] = mk[0].vf;
   Plan3T pl = plan3t(g, nf, sms, occ);
   if (!pl.ok) { cudaGetLastError(); return DN_OK; }
   if (pl.grid > 0x7fffffffLL) return DN_OK;
   const size_t need = 64 + 8 * (size_t)pl.grid;
   if (!workspace || wsb < need) return fail(DN_EWORKSPACE, "workspace too small: %zu < %zu", wsb, need);
   if ((uintptr_t)workspace % 16) return fail(DN_EWORKSPACE, "workspace must be 16-byte aligned");
+  for (int i = 0; i < nf; ++i)
+    if (!make_map(&p.tm[i], fl[i], g, pl.BX, pl.BY, &p.bmul[i])) return DN_OK;   // general kernel takes it
   p.nf = nf;
   p.B = g->batch; p.nx = g->nx; p.ny = g->ny; p.nz = g->nz;
-  p.LX = pl.LX; p.TY = pl.TY; p.nty = pl.nty; p.ZC = pl.ZC; p.nzc = pl.nzc; p.S = pl.S;
+  p.LXT = pl.LXT; p.LXo = pl.LXo; p.hl = pl.hl; p.ntx = pl.ntx;
+  p.rows = pl.rows; p.TY = pl.TY; p.nty = pl.nty;
+  p.ZC = pl.ZC; p.nzc = pl.nzc; p.S = pl.S;
+  p.BX = pl.BX; p.BY = pl.BY; p.fstride = pl.fstride;
   if (g->z_own_hi > g->z_own_lo) { p.zloss_lo = g->z_own_lo; p.zloss_hi = g->z_own_hi; }
   else { p.zloss_lo = 0; p.zloss_hi = g->nz; }
   const float t = k.t;
@@ -169,6 +232,10 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   p.red.partials = (double*)((char*)workspace + 64);
   p.red.loss_out = loss_out; p.red.loss_f32 = loss_f32;
   p.mode = mode;
+  if (env_i3("DN_DEBUG_PLAN", 0))
+    fprintf(stderr, "[plan3t] B=%d n=(%d,%d,%d) LXT=%d LXo=%d hl=%d ntx=%d rows=%d TY=%d nty=%d ZC=%d nzc=%d S=%d BX=%d BY=%d "
+            "fstride=%d threads=%d grid=%lld smem=%zu\n", g->batch, g->nx, g->ny, g->nz, pl.LXT, pl.LXo, pl.hl, pl.ntx,
+            pl.rows, pl.TY, pl.nty, pl.ZC, pl.nzc, pl.S, pl.BX, pl.BY, pl.fstride, pl.threads, pl.grid, pl.smem);
   *handled = true;
   return check_cuda(fn(p, dim3((unsigned)pl.grid), dim3(pl.threads), pl.smem, (cudaStream_t)stream),
                     "fem3d_tma launch");
