@@ -112,12 +112,13 @@ class ZSlabPoisson3D:
         return cut(u_global, self.slab)
 
     # ---------------------------------------------------------------- per step
-    def exchange_halos(self, u_local: torch.Tensor) -> None:
-        """In place: halo planes of `u_local` <- the neighbours' boundary owned planes.  Planes of a
-        contiguous (nl, ny, nx) slab are contiguous, so they are sent and received in place (no
-        staging copies); the four point-to-point ops go out as one NCCL group."""
+    def start_exchange(self, u_local: torch.Tensor):
+        """Enqueue the halo exchange (asynchronous w.r.t. the compute stream) and return the
+        pending work handles.  Planes of a contiguous (nl, ny, nx) slab are contiguous, so they are
+        sent and received in place (no staging copies); the point-to-point ops go out as one NCCL
+        group.  NCCL orders the group after everything already on the current stream."""
         if self.world == 1:
-            return
+            return []
         if not u_local.is_contiguous():
             raise ValueError("u_local must be contiguous (planes are exchanged in place)")
         s = self.slab
@@ -130,28 +131,67 @@ class ZSlabPoisson3D:
         if s.has_above:
             opsl += [dist.P2POp(dist.isend, u[o1 - 1], self._peer(+1), self.group),
                      dist.P2POp(dist.irecv, u[u.shape[0] - 1], self._peer(+1), self.group)]
-        for w in dist.batch_isend_irecv(opsl):
+        return dist.batch_isend_irecv(opsl)
+
+    def exchange_halos(self, u_local: torch.Tensor) -> None:
+        """In place: halo planes of `u_local` <- the neighbours' boundary owned planes."""
+        for w in self.start_exchange(u_local):
             w.wait()
 
     def _peer(self, d: int) -> int:
         r = self.rank + d
         return dist.get_global_rank(self.group, r) if self.group is not None else r
 
+    def _sub(self, t, a, b):
+        return None if t is None else t[a:b]
+
+    def _energy_on(self, u_local, a, b, z_own, count):
+        """The fused kernel on local planes [a, b) (views, no copies)."""
+        fields = {k: v[a:b] for k, v in self.fields.items()}
+        dirichlet = [(m[a:b], (v[a:b] if torch.is_tensor(v) else v)) for m, v in self.dirichlet]
+        g = self.geom_local
+        geom = ops.Geometry(3, g.nx, g.ny, b - a, g.hx, g.hy, g.hz, g.ngp_1d)
+        return self.energy(geom, u_local[a:b], z_own=z_own, mean_count=count, dirichlet=dirichlet,
+                           **fields, **self.consts)
+
     def loss_and_grad(self, u_local: torch.Tensor, exchange: bool = True, zero_halo_grad: bool = True,
-                      reduce_loss: bool = True):
+                      reduce_loss: bool = True, overlap: bool = False):
         """(loss, d loss / d u on this rank's slab).  With ``reduce_loss`` the loss is the GLOBAL
         value (one scalar all-reduce), identical on every rank; otherwise this rank's partial.
         The gradient is complete on the owned planes; the halo planes are zeroed unless
-        ``zero_halo_grad=False`` (their values are then partial sums nobody should use)."""
-        if exchange:
-            self.exchange_halos(u_local)
+        ``zero_halo_grad=False`` (their values are then partial sums nobody should use).
+
+        ``overlap=True`` hides the exchange behind the interior: the owned planes are processed
+        while the halo planes are in flight (their energy and the gradient of the planes strictly
+        inside), then the two 3-plane boundary pieces close the gradient of the first / last owned
+        plane and add the energy of the layer that touches the upper halo."""
         g = self.g
         count = float((g.nx - 1) * (g.ny - 1) * (g.nz - 1))
-        loss, grad = self.energy(self.geom_local, u_local, z_own=self.slab.own_local, mean_count=count,
-                                 dirichlet=self.dirichlet, **self.fields, **self.consts)
-        grad = grad.reshape(u_local.shape)
-        o0, o1 = self.slab.own_local
-        if zero_halo_grad:
+        s = self.slab
+        o0, o1 = s.own_local
+        nl = u_local.shape[0]
+        if not (overlap and exchange and self.world > 1 and (o1 - o0) >= 4):
+            if exchange:
+                self.exchange_halos(u_local)
+            loss, grad = self._energy_on(u_local, 0, nl, (o0, o1), count)
+            grad = grad.reshape(u_local.shape)
+        else:
+            pending = self.start_exchange(u_local)
+            # interior: owned planes only; every element layer between two owned planes counts
+            loss, gi = self._energy_on(u_local, o0, o1, (0, o1 - o0), count)
+            grad = torch.empty_like(u_local) if zero_halo_grad is False else torch.zeros_like(u_local)
+            grad[o0:o1] = gi.reshape((o1 - o0,) + tuple(u_local.shape[1:]))
+            for w in pending:
+                w.wait()
+            none = (1 << 20, (1 << 20) + 1)           # an ownership range that matches no layer
+            if s.has_below:       # planes o0-1, o0, o0+1: closes grad[o0]; its layers are counted elsewhere
+                _, gb = self._energy_on(u_local, o0 - 1, o0 + 2, none, count)
+                grad[o0] = gb.reshape((3,) + tuple(u_local.shape[1:]))[1]
+            if s.has_above:       # planes o1-2, o1-1, o1: closes grad[o1-1]; the layer above o1-1 is ours
+                la, ga = self._energy_on(u_local, o1 - 2, o1 + 1, (1, 2), count)
+                grad[o1 - 1] = ga.reshape((3,) + tuple(u_local.shape[1:]))[1]
+                loss = loss + la
+        if zero_halo_grad and not (overlap and exchange and self.world > 1 and (o1 - o0) >= 4):
             if o0 > 0:
                 grad[:o0].zero_()
             if o1 < grad.shape[0]:
@@ -160,6 +200,35 @@ class ZSlabPoisson3D:
             loss = loss.clone()
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
         return loss, grad
+
+    def capture(self, u_local: torch.Tensor, warmup: int = 3, **kw):
+        """Capture one whole step (halo exchange + kernel(s) + loss all-reduce) into a CUDA graph
+        bound to the storage of ``u_local`` and return ``replay() -> (loss, grad)`` (static output
+        tensors).  At these sizes a step is ~10 host-launched operations of 10-20 us each around a
+        ~100 us kernel: replaying a graph removes the host from the critical path.  NCCL
+        point-to-point and all-reduce are capturable; every rank must capture and replay in
+        lockstep.  NOTE: with world > 1 the captured NCCL send/recv group hung on this stack
+        (torch 2.11 / NCCL 2.28.9, 2 x B200) and is refused until that is understood."""
+        if self.world > 1:
+            raise NotImplementedError("graph capture of the halo exchange is disabled for world > 1")
+        if not u_local.is_cuda:
+            raise ValueError("capture() needs CUDA tensors")
+        side = torch.cuda.Stream(device=u_local.device)
+        side.wait_stream(torch.cuda.current_stream(u_local.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 2)):          # allocate workspaces / NCCL channels before capture
+                self.loss_and_grad(u_local, **kw)
+        torch.cuda.current_stream(u_local.device).wait_stream(side)
+        torch.cuda.synchronize(u_local.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            loss, grad = self.loss_and_grad(u_local, **kw)
+
+        def replay():
+            graph.replay()
+            return loss, grad
+        replay.graph = graph
+        return replay
 
     def gather_owned(self, u_local: torch.Tensor) -> torch.Tensor:
         """All ranks' owned planes concatenated in z (for checks / output)."""

@@ -43,7 +43,7 @@ def _spawn(fn, world, *args):
 
 
 # ------------------------------------------------------------------------------------ z-slabs
-NZ, NY, NX = 11, 6, 8
+NZ, NY, NX = 13, 6, 8
 
 
 def _global_problem():
@@ -102,6 +102,13 @@ def _slab_worker(rank, world, port, steps):
         assert gall.shape == gref.shape
         assert torch.allclose(gall, gref, rtol=1e-11, atol=1e-13)
         assert float(grad[:o0].abs().sum()) == 0.0 and float(grad[o1:].abs().sum()) == 0.0
+        # overlapped variant (interior while the halos are in flight, then the boundary pieces)
+        ul2 = sp.local_of(u)
+        ul2[:o0] = float("nan"); ul2[o1:] = float("nan")
+        loss2, grad2 = sp.loss_and_grad(ul2, overlap=True)
+        assert abs(float(loss2) - float(lref)) <= 1e-12 * abs(float(lref))
+        assert torch.allclose(sp.gather_owned(grad2), gref, rtol=1e-11, atol=1e-13)
+        assert float(grad2[:o0].abs().sum()) == 0.0 and float(grad2[o1:].abs().sum()) == 0.0
         # a few Adam steps on the slab == the same steps on the whole domain
         uw = u.clone().requires_grad_(True)
         optw = torch.optim.Adam([uw], lr=0.1)

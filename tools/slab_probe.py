@@ -52,6 +52,9 @@ res["kernel_only_ms"] = timeit(lambda: sp.loss_and_grad(u, exchange=False, zero_
 l = torch.zeros((), device=dev)
 res["allreduce_scalar_ms"] = timeit(lambda: dist.all_reduce(l))
 res["full_step_ms"] = timeit(lambda: sp.loss_and_grad(u, zero_halo_grad=False))
+res["full_step_overlap_ms"] = timeit(lambda: sp.loss_and_grad(u, zero_halo_grad=False, overlap=True))
+la, ga = sp.loss_and_grad(u.clone(), zero_halo_grad=True); lb, gb = sp.loss_and_grad(u.clone(), zero_halo_grad=True, overlap=True)
+res["overlap_vs_plain_loss_rel"] = abs(float(la) - float(lb)) / abs(float(la)); res["overlap_vs_plain_grad_maxabs"] = float((ga - gb).abs().max())
 if rank == 0:
     print({k: round(v, 4) for k, v in res.items()}, flush=True)
 dist.destroy_process_group()
