@@ -166,6 +166,38 @@ def oracle_step_time(name, sample_B, threads, repeats=3):
     return best, dof
 
 
+def oracle_on_gpu_time(name, dev, repeats=5):
+    """The reference's own path (conv2d/3d per Gauss point + pointwise + autograd, restated by the
+    oracle) executed on THIS GPU through cuDNN with TF32 off: what a DiffNet user gets on a B200
+    today.  A reported baseline like `cpu_baseline`, never the product path."""
+    import torch
+    from oracle import losses as OL
+    from oracle.fem import Q1Oracle
+    nsd, size, B, _, _ = WORKLOADS[name]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    o = Q1Oracle(nsd=nsd, domain_size=size)
+    for n in ("N_gp", "dN_x_gp", "dN_y_gp", "dN_z_gp"):
+        setattr(o, n, [w.to(dev) for w in getattr(o, n)])
+    o.gpw = o.gpw.to(dev)
+    d = make_inputs(name, dev, seed=99)
+    kw = call_kwargs(d)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = float("inf")
+    for i in range(repeats + 2):
+        u = d["u"].clone().requires_grad_(True)
+        torch.cuda.synchronize()
+        e0.record()
+        OL.energy_loss(o, u, **kw).backward()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del d, kw, u
+    torch.cuda.empty_cache()
+    return best * 1e-3, B * size ** nsd
+
+
 def make_inputs_cpu(name, sample_B):
     import torch
     nsd, size, B, _, _ = WORKLOADS[name]
@@ -383,6 +415,15 @@ def run_ours(args):
             best, dof = oracle_step_time(name, sB, threads)
             cpu = {"value": dof / best / 1e9, "unit": "GDOF/s", "cores": threads, "kind": "port",
                    "sample": f"oracle fwd+bwd on B={sB} of {B} samples ({dof} DOF), best of 3, torch {torch.__version__} CPU"}
+            if name != "poisson3d_256_b1":      # the conv path materialises ~20 GB of Gauss-point tensors at 256^3
+                try:
+                    tg, dg = oracle_on_gpu_time(name, dev)
+                    cpu["same_path_on_this_gpu"] = {
+                        "value": dg / tg / 1e9, "unit": "GDOF/s", "ms_per_step": tg * 1e3,
+                        "note": "the reference conv path (oracle port) on this B200 via cuDNN, TF32 off, full batch, "
+                                "best of 5 -- a baseline, not the product path"}
+                except Exception as e:   # noqa: BLE001
+                    cpu["same_path_on_this_gpu"] = {"error": f"{type(e).__name__}: {e}"}
         line = {
             "metric": "FEM loss+grad throughput", "value": value, "unit": "GDOF/s", "n_gpus": world,
             "steps": K, "warmup": max(W, 3), "ms_per_step": ms_step, "higher_is_better": True,

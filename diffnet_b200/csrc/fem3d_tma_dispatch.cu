@@ -172,9 +172,9 @@ static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ) {
 long long plan3t_max_ctas(const dn_geom* g) {
   if (g->nx % 4 != 0 || g->nx < 8) return 0;
   // workspace sizing: an upper bound on what the planner may pick -- x tiles of >= 16 pairs,
-  // y tiles owning >= 1 row when forced by env (default search: >= 1), chunks of >= 4 planes by
-  // default.  Bounded to keep the workspace small; a knob setting that needs more is refused.
-  const long long ntx = (g->nx / 2 + 15) / 16, nty = (g->ny + 1) / 2, nzc = (g->nz + 3) / 4;
+  // y tiles owning >= 1 row, chunks of >= 4 planes (the DN_T3_ZCMIN default).  Capped to keep
+  // the workspace small; a knob setting that needs more is refused with DN_EWORKSPACE.
+  const long long ntx = (g->nx / 2 + 15) / 16, nty = g->ny, nzc = (g->nz + 3) / 4;
   long long n = (long long)g->batch * ntx * nty * nzc;
   const long long cap = 1LL << 22;
   return n < cap ? n : cap;
