@@ -528,7 +528,7 @@ def run_slab(args):
     nsd, N, _, bpd, desc = WORKLOADS[name]
     h = 1.0 / (N - 1)
     geom = ops.Geometry(3, N, N, N, h, h, h, 2)
-    sp = ZSlabPoisson3D(geom)
+    sp = ZSlabPoisson3D(geom, transport=args.transport)
     sl = make_slab(N, world, rank)
     nl = sl.hi - sl.lo
     g = torch.Generator(device=dev).manual_seed(1234 + sl.lo)
@@ -546,10 +546,11 @@ def run_slab(args):
     kw = dict(zero_halo_grad=False, overlap=args.overlap)
     mode = "eager"
     replays = None
-    if not args.no_graph and world == 1:   # NCCL point-to-point inside a captured graph hung on this stack: eager for N > 1
+    # NCCL point-to-point inside a captured graph hung on this stack: graphs need the peer transport for N > 1
+    if not args.no_graph and (world == 1 or args.transport == "peer"):
         try:
             replays = [sp.capture(u, **kw) for u in us]
-            mode = "cuda_graph (exchange + kernel + all-reduce captured per step)"
+            mode = "cuda_graph (halo put/wait kernels + FEM kernel captured; loss all-reduce eager)"
         except Exception as e:   # noqa: BLE001
             replays, mode = None, f"eager (graph capture failed: {type(e).__name__}: {e})"
             torch.cuda.synchronize()
@@ -587,7 +588,7 @@ def run_slab(args):
             "config": {"workload": name, "desc": desc, "grid": [N, N, N], "slab_planes_rank0": nl,
                        "launch": mode, "l2": f"slab working set {nl * N * N * bpd / 1e6:.0f} MB per rank",
                        "timing": f"CUDA events around {K} steps, max over ranks",
-                       "parallelism": f"z-slab x{world}: ncclSend/Recv of 2 halo planes" + (" overlapped with the interior planes" if args.overlap else "") + " + loss all-reduce per step"},
+                       "parallelism": f"z-slab x{world}: " + ("NVLink peer-memory put/wait kernels (CUDA IPC)" if args.transport == "peer" else "ncclSend/Recv") + " for the 2 halo planes" + (" overlapped with the interior planes" if args.overlap else "") + " + loss all-reduce per step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_dof": bpd, "kernel": "k_fem3d_tma",
                          "note": "per-GPU: algorithmic bytes of the rank's owned planes / step time"},
@@ -606,6 +607,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="z-slab arm: halo transport (our NVLink peer-memory kernels, or NCCL send/recv)")
     ap.add_argument("--overlap", action="store_true",
                     help="z-slab arm: interior planes while the halos are in flight (3 launches instead of 1)")
     ap.add_argument("--train-steps", type=int, default=20,

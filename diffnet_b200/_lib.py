@@ -62,6 +62,14 @@ PROTOTYPES = {
     "dn_fem_gp_eval_adj_2d_f32": (C.c_int, _GPADJ_ARGS),
     "dn_fem_gp_eval_adj_3d_f32": (C.c_int, _GPADJ_ARGS),
     "dn_scale_inplace_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "dn_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "dn_peer_free": (C.c_int, [C.c_void_p]),
+    "dn_peer_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "dn_peer_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "dn_peer_unimport": (C.c_int, [C.c_void_p]),
+    "dn_peer_put_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dn_peer_wait_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

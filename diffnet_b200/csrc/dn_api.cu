@@ -12,6 +12,13 @@
 #include "gp_eval.cuh"
 
 namespace dn {
+cudaError_t launch_peer_put(float* dst_peer, const float* src, size_t n, int* remote_flag, int* local_counter,
+                            unsigned int* ticket, cudaStream_t s);
+cudaError_t launch_peer_wait(float* halo, const float* staged, size_t n, const int* flag, int* expect,
+                             long long max_spins, int* status, cudaStream_t s);
+}  // namespace dn
+
+namespace dn {
 
 static thread_local char g_err[512] = "";
 
@@ -477,6 +484,54 @@ int dn_fem_gp_eval_adj_3d_f32(const float* grad_out, const dn_geom* g, int which
   if (!grad_out || !grad_in) return fail(DN_EINVAL, "NULL input/output");
   return check_cuda(launch_gp_eval_adj(grad_out, g->batch, g->nx, g->ny, g->nz, 3, tb, grad_in,
                                        (cudaStream_t)stream), "gp_eval_adj launch");
+}
+
+int dn_peer_alloc(size_t bytes, void** ptr) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!ptr || bytes == 0) return fail(DN_EINVAL, "dn_peer_alloc: bad arguments");
+  if (int rc = check_cuda(cudaMalloc(ptr, bytes), "cudaMalloc")) return rc;
+  return check_cuda(cudaMemset(*ptr, 0, bytes), "cudaMemset");
+}
+
+int dn_peer_free(void* ptr) { return ptr ? check_cuda(cudaFree(ptr), "cudaFree") : DN_OK; }
+
+int dn_peer_export(void* ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle) return fail(DN_EINVAL, "NULL pointer");
+  cudaIpcMemHandle_t h;
+  if (int rc = check_cuda(cudaIpcGetMemHandle(&h, ptr), "cudaIpcGetMemHandle")) return rc;
+  memcpy(handle, &h, 64);
+  return DN_OK;
+}
+
+int dn_peer_import(const unsigned char handle[64], void** ptr) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!ptr || !handle) return fail(DN_EINVAL, "NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  return check_cuda(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+int dn_peer_unimport(void* ptr) { return ptr ? check_cuda(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle") : DN_OK; }
+
+int dn_peer_put_f32(float* dst_peer, const float* src, size_t n, int32_t* remote_flag, int32_t* local_counter,
+                    uint32_t* ticket, void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!dst_peer || !src || !remote_flag || !local_counter || !ticket) return fail(DN_EINVAL, "NULL pointer");
+  if (n % 4 || (uintptr_t)dst_peer % 16 || (uintptr_t)src % 16)
+    return fail(DN_EINVAL, "peer planes must be 16-byte aligned with n %% 4 == 0");
+  return check_cuda(launch_peer_put(dst_peer, src, n, remote_flag, local_counter, ticket, (cudaStream_t)stream),
+                    "peer_put launch");
+}
+
+int dn_peer_wait_f32(float* halo, const float* staged, size_t n, const int32_t* flag, int32_t* expect,
+                     int64_t max_spins, int32_t* status, void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!halo || !staged || !flag || !expect || !status) return fail(DN_EINVAL, "NULL pointer");
+  if (n % 4 || (uintptr_t)halo % 16 || (uintptr_t)staged % 16)
+    return fail(DN_EINVAL, "peer planes must be 16-byte aligned with n %% 4 == 0");
+  return check_cuda(launch_peer_wait(halo, staged, n, flag, expect, max_spins > 0 ? max_spins : (1LL << 22), status,
+                                     (cudaStream_t)stream), "peer_wait launch");
 }
 
 int dn_scale_inplace_f32(float* x, size_t n, const float* factor_dev, void* stream) {

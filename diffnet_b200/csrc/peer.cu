@@ -1,0 +1,87 @@
+// peer.cu -- halo planes over NVLink peer memory (z-slab decomposition).
+//
+// One process per GPU; each rank maps its neighbours' receive buffers (CUDA IPC) into its own
+// address space.  Per step and neighbour:
+//   k_peer_put   copies one boundary plane from local HBM straight into the neighbour's staging
+//                buffer with plain vectorised stores over NVLink (no NCCL, no host), then -- after
+//                a system-scope fence, by the last block through a ticket -- publishes the sender's
+//                step counter in the neighbour's flag word;
+//   k_peer_wait  spins (bounded) on the local flag word until the expected step has arrived and
+//                copies the staged plane into the halo plane of the local field.
+// Both are ordinary stream-ordered launches: a whole slab step (puts, waits, the FEM kernel) can
+// be captured in a CUDA graph, which NCCL point-to-point on this stack could not.
+#include "dn_common.cuh"
+
+namespace dn {
+
+__global__ void __launch_bounds__(256) k_peer_put(float4* __restrict__ dst, const float4* __restrict__ src,
+                                                  long long n4, int* remote_flag, int* local_counter,
+                                                  unsigned int* ticket) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) dst[i] = src[i];
+  __threadfence_system();                      // this thread's peer stores are visible system-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {                  // every block has fenced its stores
+      *ticket = 0u;
+      const int step = *local_counter + 1;
+      *local_counter = step;
+      __threadfence_system();
+      *reinterpret_cast<volatile int*>(remote_flag) = step;
+    }
+  }
+}
+
+// status: 0 = ok; on time-out the kernel writes 1 there and still copies (the caller checks it
+// when it next synchronises) -- a lost neighbour must not hang the GPU.
+__global__ void __launch_bounds__(256) k_peer_wait(float4* __restrict__ halo, const float4* __restrict__ staged,
+                                                   long long n4, const int* flag, int* expect,
+                                                   long long max_spins, int* status) {
+  __shared__ int want;
+  if (threadIdx.x == 0) {
+    want = *expect + 1;
+    long long spins = 0;
+    while (*reinterpret_cast<const volatile int*>(flag) < want) {
+      if (++spins > max_spins) { *status = 1; break; }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) halo[i] = staged[i];
+  // the LAST block to finish bumps the expectation (same ticket idea, on the status word's neighbour)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(reinterpret_cast<unsigned int*>(status) + 1, 1u);
+    if (t == gridDim.x - 1) {
+      reinterpret_cast<unsigned int*>(status)[1] = 0u;
+      *expect = want;
+    }
+  }
+}
+
+cudaError_t launch_peer_put(float* dst_peer, const float* src, size_t n, int* remote_flag, int* local_counter,
+                            unsigned int* ticket, cudaStream_t s) {
+  const long long n4 = (long long)(n / 4);
+  int grid = (int)((n4 + 255) / 256);
+  if (grid > 64) grid = 64;
+  if (grid < 1) grid = 1;
+  k_peer_put<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(dst_peer), reinterpret_cast<const float4*>(src), n4,
+                                  remote_flag, local_counter, ticket);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_peer_wait(float* halo, const float* staged, size_t n, const int* flag, int* expect,
+                             long long max_spins, int* status, cudaStream_t s) {
+  const long long n4 = (long long)(n / 4);
+  int grid = (int)((n4 + 255) / 256);
+  if (grid > 32) grid = 32;
+  if (grid < 1) grid = 1;
+  k_peer_wait<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(halo), reinterpret_cast<const float4*>(staged), n4,
+                                   flag, expect, max_spins, status);
+  return cudaGetLastError();
+}
+
+}  // namespace dn

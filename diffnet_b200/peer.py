@@ -1,0 +1,114 @@
+"""Halo planes over NVLink peer memory (one process per GPU, CUDA IPC) -- the transport of
+``slab.ZSlabPoisson3D(transport="peer")``.
+
+Each rank owns one receive allocation (``dn_peer_alloc``: a raw cudaMalloc, because an IPC handle
+names a whole allocation): staging planes ``[parity][side][ny*nx]`` and flag words
+``[parity][side]``; its IPC handle is exchanged once (``all_gather_object``) and the two
+neighbours map it (``dn_peer_import``, opened on the ACCESSING device).  A step is then four stream-ordered launches of our own kernels
+(``dn_peer_put_f32`` x2: stores over NVLink + release of the step counter in the neighbour's flag;
+``dn_peer_wait_f32`` x2: bounded device-side wait + copy into the local halo plane) -- no NCCL
+call, no host synchronisation, and capturable in a CUDA graph.  Double-buffering by step parity
+makes the write-after-read hazards impossible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+BELOW, ABOVE = 0, 1
+
+
+class PeerHalo:
+    def __init__(self, slab, ny: int, nx: int, device: torch.device, group=None, max_spins: int = 1 << 22):
+        if (ny * nx) % 4:
+            raise L.DiffNetFEMError("peer halo planes need ny*nx % 4 == 0")
+        self.slab, self.plane, self.device, self.group = slab, ny * nx, device, group
+        self.max_spins = max_spins
+        self.parity = 0
+        plane = self.plane
+        self._nbytes = 2 * 2 * plane * 4
+        lib = L.lib()
+        # local control words per (parity, side): [send counter, put ticket, expect, -, status, wait ticket, -, -]
+        self.ctrl = torch.zeros(2, 2, 8, dtype=torch.int32, device=device)
+        self._recv = C.c_void_p()
+        self._imported = {}
+        with torch.cuda.device(device):
+            L.check(lib.dn_peer_alloc(self._nbytes + 256, C.byref(self._recv)), "dn_peer_alloc")
+            handle = C.create_string_buffer(64)
+            L.check(lib.dn_peer_export(self._recv, handle), "dn_peer_export")
+        torch.cuda.synchronize(device)
+        world = dist.get_world_size(group)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        for side, r in ((BELOW, slab.rank - 1), (ABOVE, slab.rank + 1)):
+            if 0 <= r < world:
+                ptr = C.c_void_p()
+                with torch.cuda.device(device):
+                    L.check(lib.dn_peer_import(handles[r], C.byref(ptr)), "dn_peer_import")
+                self._imported[side] = ptr
+        dist.barrier(group=group)                          # everyone mapped before anyone writes
+
+    def close(self):
+        lib = L.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for ptr in self._imported.values():
+                lib.dn_peer_unimport(ptr)
+            self._imported = {}
+            if self._recv:
+                lib.dn_peer_free(self._recv)
+                self._recv = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    def _local_ptrs(self, side: int, parity: int):
+        slot = parity * 2 + side
+        return self._recv.value + slot * self.plane * 4, self._recv.value + self._nbytes + slot * 4
+
+    def _peer_ptrs(self, side: int, parity: int):
+        """(staging plane, flag word) in the neighbour on `side`, where I am its OTHER side."""
+        base = self._imported[side].value
+        slot = parity * 2 + (1 - side)
+        return base + slot * self.plane * 4, base + self._nbytes + slot * 4
+
+    def exchange(self, u_local: torch.Tensor) -> None:
+        """Refresh the halo planes of the contiguous (nl, ny, nx) slab `u_local` in place."""
+        s = self.slab
+        o0, o1 = s.own_local
+        nl = u_local.shape[0]
+        p = self.parity
+        self.parity ^= 1
+        lib = L.lib()
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        u = u_local.detach()
+        esz = 4 * self.plane
+        with torch.cuda.device(self.device):
+            for side, has, src_plane in ((BELOW, s.has_below, o0), (ABOVE, s.has_above, o1 - 1)):
+                if not has:
+                    continue
+                dst, flag = self._peer_ptrs(side, p)
+                c = self.ctrl[p, side]
+                L.check(lib.dn_peer_put_f32(C.c_void_p(dst), C.c_void_p(u.data_ptr() + src_plane * esz), self.plane,
+                                            C.c_void_p(flag), C.c_void_p(c.data_ptr()), C.c_void_p(c.data_ptr() + 4),
+                                            stream), "dn_peer_put_f32")
+            for side, has, halo_plane in ((BELOW, s.has_below, 0), (ABOVE, s.has_above, nl - 1)):
+                if not has:
+                    continue
+                c = self.ctrl[p, side]
+                staged, flag = self._local_ptrs(side, p)
+                L.check(lib.dn_peer_wait_f32(C.c_void_p(u.data_ptr() + halo_plane * esz),
+                                             C.c_void_p(staged), self.plane,
+                                             C.c_void_p(flag), C.c_void_p(c.data_ptr() + 8),
+                                             self.max_spins, C.c_void_p(c.data_ptr() + 16), stream), "dn_peer_wait_f32")
+
+    def timed_out(self) -> bool:
+        """True if any device-side wait hit its poll limit (synchronises)."""
+        return bool(self.ctrl[:, :, 4].any().item())

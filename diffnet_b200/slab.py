@@ -83,7 +83,8 @@ class ZSlabPoisson3D:
     ``u_local`` is this rank's (hi-lo, ny, nx) slab INCLUDING halos; only the owned planes are
     optimisation variables, the halos are refreshed from the neighbours at every step."""
 
-    def __init__(self, geom_global: ops.Geometry, group=None, energy: Optional[Callable] = None):
+    def __init__(self, geom_global: ops.Geometry, group=None, energy: Optional[Callable] = None,
+                 transport: str = "nccl"):
         if geom_global.nsd != 3:
             raise ValueError("z-slab decomposition is for 3-D meshes")
         self.g = geom_global
@@ -95,6 +96,10 @@ class ZSlabPoisson3D:
         self.geom_local = ops.Geometry(3, geom_global.nx, geom_global.ny, nl, geom_global.hx, geom_global.hy,
                                        geom_global.hz, geom_global.ngp_1d)
         self.energy = energy or _default_energy
+        if transport not in ("nccl", "peer"):
+            raise ValueError("transport must be 'nccl' (send/recv) or 'peer' (NVLink peer memory, CUDA only)")
+        self.transport = transport
+        self._peer_halo = None                 # PeerHalo, created at the first exchange (needs the device)
         self.fields = {}
         self.dirichlet: Sequence = ()
         self.consts = {}
@@ -135,6 +140,14 @@ class ZSlabPoisson3D:
 
     def exchange_halos(self, u_local: torch.Tensor) -> None:
         """In place: halo planes of `u_local` <- the neighbours' boundary owned planes."""
+        if self.transport == "peer" and self.world > 1:
+            if not u_local.is_contiguous():
+                raise ValueError("u_local must be contiguous (planes are exchanged in place)")
+            if self._peer_halo is None:
+                from .peer import PeerHalo
+                self._peer_halo = PeerHalo(self.slab, self.g.ny, self.g.nx, u_local.device, self.group)
+            self._peer_halo.exchange(u_local)
+            return
         for w in self.start_exchange(u_local):
             w.wait()
 
@@ -201,33 +214,50 @@ class ZSlabPoisson3D:
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
         return loss, grad
 
-    def capture(self, u_local: torch.Tensor, warmup: int = 3, **kw):
-        """Capture one whole step (halo exchange + kernel(s) + loss all-reduce) into a CUDA graph
-        bound to the storage of ``u_local`` and return ``replay() -> (loss, grad)`` (static output
-        tensors).  At these sizes a step is ~10 host-launched operations of 10-20 us each around a
-        ~100 us kernel: replaying a graph removes the host from the critical path.  NCCL
-        point-to-point and all-reduce are capturable; every rank must capture and replay in
-        lockstep.  NOTE: with world > 1 the captured NCCL send/recv group hung on this stack
-        (torch 2.11 / NCCL 2.28.9, 2 x B200) and is refused until that is understood."""
-        if self.world > 1:
-            raise NotImplementedError("graph capture of the halo exchange is disabled for world > 1")
+    def capture(self, u_local: torch.Tensor, warmup: int = 4, **kw):
+        """Capture whole steps (halo exchange + kernel(s)) into CUDA graphs bound to the storage of
+        ``u_local`` and return ``replay() -> (loss, grad)`` (static output tensors).  At these sizes a
+        step is ~10 host-launched operations of 10-20 us each around a ~100 us kernel: replaying a
+        graph removes the host from the critical path.  Every rank must capture and replay in
+        lockstep.  With world > 1 this needs ``transport="peer"`` (our own put/wait kernels are
+        plain launches; the captured NCCL send/recv group hung on this stack: torch 2.11 /
+        NCCL 2.28.9, 2 x B200), two graphs are captured (one per halo parity) and replayed
+        alternately, and the scalar loss all-reduce stays OUTSIDE the graph."""
         if not u_local.is_cuda:
             raise ValueError("capture() needs CUDA tensors")
-        side = torch.cuda.Stream(device=u_local.device)
-        side.wait_stream(torch.cuda.current_stream(u_local.device))
+        if self.world > 1 and self.transport != "peer":
+            raise NotImplementedError("graph capture with world > 1 needs transport='peer'")
+        reduce_loss = kw.pop("reduce_loss", True)
+        dev = u_local.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(max(warmup, 2)):          # allocate workspaces / NCCL channels before capture
-                self.loss_and_grad(u_local, **kw)
-        torch.cuda.current_stream(u_local.device).wait_stream(side)
-        torch.cuda.synchronize(u_local.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            loss, grad = self.loss_and_grad(u_local, **kw)
+            for _ in range(2 * max(warmup // 2, 1)):      # even count: parity back to 0; allocates workspaces
+                self.loss_and_grad(u_local, reduce_loss=False, **kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graphs, outs = [], []
+        for _ in range(2 if self.world > 1 else 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                outs.append(self.loss_and_grad(u_local, reduce_loss=False, **kw))
+            graphs.append(g)
+            # the capture advanced the host-side parity but ran nothing: run the step for real so
+            # that both ranks' device-side counters stay in step with the parity sequence
+            g.replay()
+        torch.cuda.synchronize(dev)
+        state = {"i": 0}
 
         def replay():
-            graph.replay()
+            i = state["i"]
+            state["i"] = (i + 1) % len(graphs)
+            graphs[i].replay()
+            loss, grad = outs[i]
+            if reduce_loss and self.world > 1:
+                loss = loss.clone()
+                dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
             return loss, grad
-        replay.graph = graph
+        replay.graphs = graphs
         return replay
 
     def gather_owned(self, u_local: torch.Tensor) -> torch.Tensor:

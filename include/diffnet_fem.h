@@ -20,6 +20,8 @@
  *   dn_fem_gp_eval_adj_*        (DiffNetFEM.py:7-18,143-156) and their autograd backward
  *                               (convolution_backward = scatter-transpose).
  *   dn_scale_inplace_f32        autograd's  grad_input = grad_output * dL/du.
+ *   dn_peer_{put,wait}_f32      (no reference counterpart) one-plane halo exchange of the z-slab
+ *                               decomposition through NVLink peer memory.
  *
  * Conventions
  *   - All pointers in dn_field / outputs are DEVICE pointers, fp32, x (innermost) contiguous.
@@ -164,6 +166,36 @@ int dn_fem_gp_eval_adj_3d_f32(const float* grad_out, const dn_geom* g, int which
 /* x[i] *= *factor_dev for i < n, skipping all memory traffic when *factor_dev == 1.0f
  * (the usual loss.backward() case).  factor_dev is a device pointer: no host sync. */
 int dn_scale_inplace_f32(float* x, size_t n, const float* factor_dev, void* stream);
+
+/*
+ * Halo planes over NVLink peer memory (z-slab decomposition of one 3-D field over several GPUs,
+ * one process per GPU; new functionality, SURVEY.md 8e -- the reference is single-GPU there).
+ *
+ * dn_peer_put_f32: copy n floats (n % 4 == 0, 16-byte aligned) from `src` (local) to `dst_peer`
+ *   (a buffer of the neighbouring GPU mapped into this process, e.g. through CUDA IPC) with
+ *   stores over NVLink, then publish ++(*local_counter) in `*remote_flag` (a word in the
+ *   neighbour's memory) with system-scope release ordering.  `ticket`: a zero-initialised local
+ *   device word (scratch).
+ * dn_peer_wait_f32: wait (on the device, bounded by max_spins polls; no host involvement) until
+ *   *flag >= ++(*expect), then copy the staged plane into `halo` (both local).  `status`: two
+ *   zero-initialised local device ints; status[0] becomes 1 if the wait timed out.
+ * Both are asynchronous on `stream` and may be captured in a CUDA graph.
+ */
+/* Receive buffers for the peer transport.  They are the one thing this library allocates (a raw
+ * cudaMalloc on the current device, zero-filled, owned by the caller through dn_peer_free): a CUDA
+ * IPC handle must name a whole allocation, which a framework's caching allocator does not hand
+ * out.  dn_peer_export writes the 64-byte IPC handle; dn_peer_import maps a neighbour's buffer
+ * into THIS process for access from the CURRENT device (peer access is enabled as needed);
+ * dn_peer_unimport unmaps it. */
+int dn_peer_alloc(size_t bytes, void** ptr);
+int dn_peer_free(void* ptr);
+int dn_peer_export(void* ptr, unsigned char handle[64]);
+int dn_peer_import(const unsigned char handle[64], void** ptr);
+int dn_peer_unimport(void* ptr);
+int dn_peer_put_f32(float* dst_peer, const float* src, size_t n, int32_t* remote_flag,
+                    int32_t* local_counter, uint32_t* ticket, void* stream);
+int dn_peer_wait_f32(float* halo, const float* staged, size_t n, const int32_t* flag, int32_t* expect,
+                     int64_t max_spins, int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }
