@@ -214,3 +214,19 @@ def test_z_slab_ownership_matches_whole_domain():
         parts.append(g[:, z0 - lo:z1 - lo])
     assert rel_scalar(total, float(loss)) < 1e-5
     assert rel_l2(torch.cat(parts, 1), grad) < 1e-6
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node")
+def test_peer_memory_halo_transport_two_gpus():
+    """tools/slab_peer_check.py under torchrun on 2 GPUs: the NVLink peer-memory transport
+    (dn_peer_put/wait) gives bit-identical loss, gradient and refreshed halos to NCCL send/recv,
+    eagerly and replayed from CUDA graphs."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tools", "slab_peer_check.py"), "64"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "'loss_equal': True" in r.stdout and "'grad_equal': True" in r.stdout and "'u_equal': True" in r.stdout
