@@ -30,7 +30,8 @@
  *     broadcasts one field over the batch.
  *   - Outputs (grad_u, grad_nu, residual, gp-eval results) are dense/contiguous.
  *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
- *     allocates nothing and keeps no device state.  The caller owns all buffers.
+ *     allocates nothing and keeps no device state.  The caller owns all buffers.  (Only
+ *     dn_peer_alloc/dn_peer_import hand out memory; they are synchronous set-up calls.)
  *   - `workspace`: at least dn_fem_workspace_bytes() bytes, 16-byte aligned, and ZERO-FILLED
  *     BEFORE ITS FIRST USE; a call leaves it zero-filled-equivalent for the next call on the same
  *     stream (the ticket counter self-resets).  Do not share one workspace between streams.
