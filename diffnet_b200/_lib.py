@@ -68,6 +68,8 @@ PROTOTYPES = {
     "dn_peer_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "dn_peer_unimport": (C.c_int, [C.c_void_p]),
     "dn_peer_put_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dn_peer_allreduce_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_void_p]),
     "dn_peer_wait_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_void_p]),
 }

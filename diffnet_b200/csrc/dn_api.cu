@@ -16,6 +16,9 @@ cudaError_t launch_peer_put(float* dst_peer, const float* src, size_t n, int* re
                             unsigned int* ticket, cudaStream_t s);
 cudaError_t launch_peer_wait(float* halo, const float* staged, size_t n, const int* flag, int* expect,
                              long long max_spins, int* status, cudaStream_t s);
+cudaError_t launch_peer_allreduce(const float* partial, float* out, double* slots, double* const* peer_slots,
+                                  int rank, int world, int* counter, long long max_spins, int* status,
+                                  cudaStream_t s);
 }  // namespace dn
 
 namespace dn {
@@ -532,6 +535,16 @@ int dn_peer_wait_f32(float* halo, const float* staged, size_t n, const int32_t* 
     return fail(DN_EINVAL, "peer planes must be 16-byte aligned with n %% 4 == 0");
   return check_cuda(launch_peer_wait(halo, staged, n, flag, expect, max_spins > 0 ? max_spins : (1LL << 22), status,
                                      (cudaStream_t)stream), "peer_wait launch");
+}
+
+int dn_peer_allreduce_f32(const float* partial, float* out, double* slots, double* const* peer_slots, int rank,
+                          int world, int32_t* counter, int64_t max_spins, int32_t* status, void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!partial || !out || !slots || !peer_slots || !counter || !status) return fail(DN_EINVAL, "NULL pointer");
+  if (world < 1 || world > 32 || rank < 0 || rank >= world) return fail(DN_EINVAL, "bad rank/world %d/%d", rank, world);
+  return check_cuda(launch_peer_allreduce(partial, out, slots, peer_slots, rank, world, counter,
+                                          max_spins > 0 ? max_spins : (1LL << 22), status, (cudaStream_t)stream),
+                    "peer_allreduce launch");
 }
 
 int dn_scale_inplace_f32(float* x, size_t n, const float* factor_dev, void* stream) {

@@ -93,12 +93,13 @@ static size_t smem_3t(int S, int nf, int fstride, int threads) {
 //   SM time ~ ceil(grid / SMs) * threads * (ZC + 1)   [thread-layers executed by the busiest SM]
 // with a penalty when fewer than 12 warps per SM are resident and a mild preference for one wave.
 // `occ` may be null (workspace sizing): then the register bound is assumed.
-static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ) {
+static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_variant) {
   Plan3T best;
   memset(&best, 0, sizeof(best));
   if (g->nx % 4 != 0 || g->nx < 8) return best;
   const int npairs = g->nx / 2;
-  const int maxt = env_i3("DN_T3_THREADS", DN_T3_MAXT);
+  int maxt = env_i3("DN_T3_THREADS", maxt_variant);
+  if (maxt > maxt_variant) maxt = maxt_variant;
   const int lx_forced = env_i3("DN_T3_LX", 0), ty_forced = env_i3("DN_T3_TY", 0), zc_forced = env_i3("DN_T3_ZC", 0);
   int zmin = env_i3("DN_T3_ZCMIN", 4);
   if (zmin < 1) zmin = 1;
@@ -131,7 +132,7 @@ static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ) {
       const int BY = TY + 2;
       if (BY > 256) continue;
       const int threads = (rows * LXT + 31) / 32 * 32;
-      if (threads > DN_T3_MAXT) continue;
+      if (threads > maxt_variant) continue;
       const int fstride = (BX * BY + 31) / 32 * 32;
       int S = S0;
       while (S > 2 && smem_3t(S, nf, fstride, threads) > (size_t)kMaxDynSmem) --S;
@@ -202,7 +203,7 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   if (NMK) fl[nf++] = numask;
   for (int i = 0; i < nmasks; ++i) { fl[nf++] = mk[i].m; p.mval[i] = mk[i].v; }
   if (MK == 4) fl[nf++] = mk[0].vf;
-  Plan3T pl = plan3t(g, nf, sms, occ);
+  Plan3T pl = plan3t(g, nf, sms, occ, DN_T3_MAXT_OF(NU));
   if (!pl.ok) { cudaGetLastError(); return DN_OK; }
   if (pl.grid > 0x7fffffffLL) return DN_OK;
   const size_t need = 64 + 8 * (size_t)pl.grid;

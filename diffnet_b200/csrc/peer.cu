@@ -62,6 +62,46 @@ __global__ void __launch_bounds__(256) k_peer_wait(float4* __restrict__ halo, co
   }
 }
 
+// Sum of one float per rank over all ranks, through peer memory, in RANK ORDER (bit-identical on
+// every rank and from run to run).  `slots`: this rank's receive area, double[world] values then
+// int[world] flags (one pair of areas per parity, chosen by the caller); `peer_slots[r]`: the same
+// area of rank r mapped here (entry `rank` unused).  One CTA of 32 threads; world <= 32.
+__global__ void __launch_bounds__(32) k_peer_allreduce(const float* __restrict__ partial, float* __restrict__ out,
+                                                       double* slots, double* const* peer_slots, int rank,
+                                                       int world, int* counter, long long max_spins,
+                                                       int* status) {
+  const int t = threadIdx.x;
+  const int step = *counter + 1;
+  const double mine = (double)*partial;
+  int* flags = reinterpret_cast<int*>(slots + world);
+  if (t < world && t != rank) {
+    double* ps = peer_slots[t];
+    ps[rank] = mine;
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(reinterpret_cast<int*>(ps + world) + rank) = step;
+    long long spins = 0;
+    while (*reinterpret_cast<volatile int*>(flags + t) < step) {
+      if (++spins > max_spins) { *status = 1; break; }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (t == 0) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += (r == rank) ? mine : *reinterpret_cast<volatile double*>(slots + r);
+    *out = (float)s;
+    *counter = step;
+  }
+}
+
+cudaError_t launch_peer_allreduce(const float* partial, float* out, double* slots, double* const* peer_slots,
+                                  int rank, int world, int* counter, long long max_spins, int* status,
+                                  cudaStream_t s) {
+  k_peer_allreduce<<<1, 32, 0, s>>>(partial, out, slots, peer_slots, rank, world, counter, max_spins, status);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_peer_put(float* dst_peer, const float* src, size_t n, int* remote_flag, int* local_counter,
                             unsigned int* ticket, cudaStream_t s) {
   const long long n4 = (long long)(n / 4);

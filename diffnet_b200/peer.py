@@ -31,34 +31,50 @@ class PeerHalo:
         self.parity = 0
         plane = self.plane
         self._nbytes = 2 * 2 * plane * 4
+        world = dist.get_world_size(group)
+        self.world = world
+        # after the planes and the 4 halo flags (256 B): two all-reduce areas (parity), each double[world] + int32[world]
+        self._red_off = self._nbytes + 256
+        self._red_area = (8 * world + 4 * world + 15) // 16 * 16
         lib = L.lib()
         # local control words per (parity, side): [send counter, put ticket, expect, -, status, wait ticket, -, -]
         self.ctrl = torch.zeros(2, 2, 8, dtype=torch.int32, device=device)
         self._recv = C.c_void_p()
         self._imported = {}
         with torch.cuda.device(device):
-            L.check(lib.dn_peer_alloc(self._nbytes + 256, C.byref(self._recv)), "dn_peer_alloc")
+            L.check(lib.dn_peer_alloc(self._red_off + 2 * self._red_area, C.byref(self._recv)), "dn_peer_alloc")
             handle = C.create_string_buffer(64)
             L.check(lib.dn_peer_export(self._recv, handle), "dn_peer_export")
         torch.cuda.synchronize(device)
-        world = dist.get_world_size(group)
         handles = [None] * world
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        for side, r in ((BELOW, slab.rank - 1), (ABOVE, slab.rank + 1)):
-            if 0 <= r < world:
+        self._all = {}                                     # rank -> mapped base pointer (every other rank)
+        for r in range(world):
+            if r != slab.rank:
                 ptr = C.c_void_p()
                 with torch.cuda.device(device):
                     L.check(lib.dn_peer_import(handles[r], C.byref(ptr)), "dn_peer_import")
-                self._imported[side] = ptr
+                self._all[r] = ptr
+        for side, r in ((BELOW, slab.rank - 1), (ABOVE, slab.rank + 1)):
+            if 0 <= r < world:
+                self._imported[side] = self._all[r]
+        # device tables of the peers' all-reduce areas, one per parity; control words for the reduction
+        self._red_tables = []
+        for par in range(2):
+            ptrs = [(self._all[r].value if r != slab.rank else self._recv.value) + self._red_off + par * self._red_area
+                    for r in range(world)]
+            self._red_tables.append(torch.tensor(ptrs, dtype=torch.int64, device=device))
+        self.red_ctrl = torch.zeros(2, 4, dtype=torch.int32, device=device)       # per parity: [counter, status, -, -]
+        self.red_parity = 0
         dist.barrier(group=group)                          # everyone mapped before anyone writes
 
     def close(self):
         lib = L.lib()
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)
-            for ptr in self._imported.values():
+            for ptr in self._all.values():
                 lib.dn_peer_unimport(ptr)
-            self._imported = {}
+            self._all, self._imported = {}, {}
             if self._recv:
                 lib.dn_peer_free(self._recv)
                 self._recv = C.c_void_p()
@@ -109,6 +125,23 @@ class PeerHalo:
                                              C.c_void_p(flag), C.c_void_p(c.data_ptr() + 8),
                                              self.max_spins, C.c_void_p(c.data_ptr() + 16), stream), "dn_peer_wait_f32")
 
+    def allreduce_sum(self, partial: torch.Tensor) -> torch.Tensor:
+        """Sum of a 0-dim fp32 device tensor over all ranks through peer memory (rank order, so the
+        result is bit-identical everywhere); stream-ordered, graph-capturable, no NCCL."""
+        p = self.red_parity
+        self.red_parity ^= 1
+        out = torch.empty_like(partial)
+        lib = L.lib()
+        c = self.red_ctrl[p]
+        with torch.cuda.device(self.device):
+            L.check(lib.dn_peer_allreduce_f32(
+                C.c_void_p(partial.data_ptr()), C.c_void_p(out.data_ptr()),
+                C.c_void_p(self._recv.value + self._red_off + p * self._red_area),
+                C.c_void_p(self._red_tables[p].data_ptr()), self.slab.rank, self.world, C.c_void_p(c.data_ptr()),
+                self.max_spins, C.c_void_p(c.data_ptr() + 4),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "dn_peer_allreduce_f32")
+        return out
+
     def timed_out(self) -> bool:
         """True if any device-side wait hit its poll limit (synchronises)."""
-        return bool(self.ctrl[:, :, 4].any().item())
+        return bool(self.ctrl[:, :, 4].any().item()) or bool(self.red_ctrl[:, 1].any().item())

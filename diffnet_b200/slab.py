@@ -210,53 +210,78 @@ class ZSlabPoisson3D:
             if o1 < grad.shape[0]:
                 grad[o1:].zero_()
         if reduce_loss and self.world > 1:
-            loss = loss.clone()
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+            loss = self._reduce(loss, u_local)
         return loss, grad
 
-    def capture(self, u_local: torch.Tensor, warmup: int = 4, **kw):
-        """Capture whole steps (halo exchange + kernel(s)) into CUDA graphs bound to the storage of
-        ``u_local`` and return ``replay() -> (loss, grad)`` (static output tensors).  At these sizes a
-        step is ~10 host-launched operations of 10-20 us each around a ~100 us kernel: replaying a
-        graph removes the host from the critical path.  Every rank must capture and replay in
-        lockstep.  With world > 1 this needs ``transport="peer"`` (our own put/wait kernels are
-        plain launches; the captured NCCL send/recv group hung on this stack: torch 2.11 /
-        NCCL 2.28.9, 2 x B200), two graphs are captured (one per halo parity) and replayed
-        alternately, and the scalar loss all-reduce stays OUTSIDE the graph."""
-        if not u_local.is_cuda:
+    def _reduce(self, loss, u_local):
+        if self.transport == "peer" and loss.is_cuda:
+            if self._peer_halo is None:
+                from .peer import PeerHalo
+                self._peer_halo = PeerHalo(self.slab, self.g.ny, self.g.nx, u_local.device, self.group)
+            return self._peer_halo.allreduce_sum(loss.reshape(()).float())
+        loss = loss.clone()
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        return loss
+
+    def _parity(self):
+        return self._peer_halo.parity if self._peer_halo is not None else 0
+
+    def _set_parity(self, p: int):
+        if self._peer_halo is not None:
+            self._peer_halo.parity = p
+            self._peer_halo.red_parity = p
+
+    def capture(self, u_locals, warmup: int = 4, **kw):
+        """Capture whole steps (halo exchange + kernel(s) + loss all-reduce) into CUDA graphs and
+        return ``replay() -> (loss, grad)`` (static output tensors of the step just replayed).
+        ``u_locals``: one slab tensor or a list of them (the graphs are bound to their storage and
+        replayed round-robin: rotating input sets for benchmarks).  At these sizes a step is ~10
+        host-launched operations of 10-20 us each around a ~100 us kernel: replaying a graph removes
+        the host from the critical path.  Every rank must capture and replay in lockstep.  With
+        world > 1 this needs ``transport="peer"`` (our put/wait/all-reduce kernels are plain
+        launches; the captured NCCL send/recv group hung on this stack: torch 2.11 / NCCL 2.28.9,
+        2 x B200).  The halo double-buffering parity is part of each graph: graph i uses parity
+        i % 2 (an even number of graphs is captured), and replay() keeps the host-side parity in
+        step so that eager calls may be mixed in between."""
+        us = list(u_locals) if isinstance(u_locals, (list, tuple)) else [u_locals]
+        if not all(u.is_cuda for u in us):
             raise ValueError("capture() needs CUDA tensors")
         if self.world > 1 and self.transport != "peer":
             raise NotImplementedError("graph capture with world > 1 needs transport='peer'")
         reduce_loss = kw.pop("reduce_loss", True)
-        dev = u_local.device
+        dev = us[0].device
+        ngraphs = len(us) if (self.world == 1 or len(us) % 2 == 0) else 2 * len(us)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(2 * max(warmup // 2, 1)):      # even count: parity back to 0; allocates workspaces
-                self.loss_and_grad(u_local, reduce_loss=False, **kw)
+            for i in range(2 * max(warmup // 2, 1)):      # allocates workspaces, maps the peers; even count
+                self.loss_and_grad(us[i % len(us)], reduce_loss=reduce_loss, **kw)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        start = self._parity()
         graphs, outs = [], []
-        for _ in range(2 if self.world > 1 else 1):
+        for i in range(ngraphs):
+            self._set_parity((start + i) % 2)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
-                outs.append(self.loss_and_grad(u_local, reduce_loss=False, **kw))
+                outs.append(self.loss_and_grad(us[i % len(us)], reduce_loss=reduce_loss, **kw))
             graphs.append(g)
-            # the capture advanced the host-side parity but ran nothing: run the step for real so
-            # that both ranks' device-side counters stay in step with the parity sequence
+            # the capture ran nothing: run the step for real so that every rank's device-side
+            # counters advance exactly as the parity sequence says
             g.replay()
+        self._set_parity((start + ngraphs) % 2)
         torch.cuda.synchronize(dev)
         state = {"i": 0}
 
         def replay():
             i = state["i"]
-            state["i"] = (i + 1) % len(graphs)
+            if self.world > 1 and self._parity() != (start + i) % 2:
+                raise RuntimeError("graph replay out of step with the halo parity (an odd number of eager "
+                                   "steps was mixed in); run one more eager step or re-capture")
             graphs[i].replay()
-            loss, grad = outs[i]
-            if reduce_loss and self.world > 1:
-                loss = loss.clone()
-                dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
-            return loss, grad
+            state["i"] = (i + 1) % ngraphs
+            self._set_parity((start + i + 1) % 2)
+            return outs[i]
         replay.graphs = graphs
         return replay
 

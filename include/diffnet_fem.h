@@ -198,6 +198,18 @@ int dn_peer_put_f32(float* dst_peer, const float* src, size_t n, int32_t* remote
 int dn_peer_wait_f32(float* halo, const float* staged, size_t n, const int32_t* flag, int32_t* expect,
                      int64_t max_spins, int32_t* status, void* stream);
 
+/*
+ * All-reduce (sum) of one float per rank through peer memory, summed in rank order (bit-identical
+ * on every rank).  `slots`: local receive area = double[world] followed by int32[world], zero-
+ * initialised, 8-byte aligned; `peer_slots`: DEVICE array of `world` pointers to the same area of
+ * every rank as mapped in this process (entry `rank` ignored); `counter`, `status`: local device
+ * words (zero-initialised).  Consecutive calls must alternate between two slot areas (parity) so a
+ * fast rank cannot overwrite values a slow rank has not read yet.  world <= 32.
+ */
+int dn_peer_allreduce_f32(const float* partial, float* out, double* slots, double* const* peer_slots,
+                          int rank, int world, int32_t* counter, int64_t max_spins, int32_t* status,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,9 +53,14 @@ for transport in ("nccl", "peer"):
         res["peer_graph_ms"] = timeit(rp)
         rp2 = sp.capture(u, zero_halo_grad=False, reduce_loss=False)
         res["peer_graph_noallreduce_ms"] = timeit(rp2)
-        lg, gg = rp()
+        lg, gg = rp2()
+        lg, gg = rp2()
+        lg = sp._reduce(lg, u)
         torch.cuda.synchronize()
         le, ge = sp.loss_and_grad(u, zero_halo_grad=False)
+        le2, _ = sp.loss_and_grad(u, zero_halo_grad=False)
+        ln_ = le.clone(); dist.all_reduce(ln_)                # NCCL sum of the (already global) value
+        res["peer_allreduce_vs_nccl_rel"] = abs(float(ln_) / world - float(le)) / abs(float(le))
         res["graph_vs_eager_loss_rel"] = abs(float(lg) - float(le)) / abs(float(le))
         res["graph_vs_eager_grad_max"] = float((gg - ge)[sp.slab.own_local[0]:sp.slab.own_local[1]].abs().max())
         assert not sp._peer_halo.timed_out(), "device-side wait timed out (graph)"
