@@ -103,6 +103,31 @@ def _new_out(shape, device, dtype=torch.float32) -> torch.Tensor:
 
 
 _workspaces = {}
+_ws_bytes = {}
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` costs ~10 us per call; skip it when `dev` is already current
+    (the one-process-per-GPU case)."""
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+def _workspace_for(lib, g, geom, B, device, stream_ptr):
+    key = (geom.nsd, B, geom.nx, geom.ny, geom.nz)
+    n = _ws_bytes.get(key)
+    if n is None:
+        n = _ws_bytes[key] = lib.dn_fem_workspace_bytes(C.byref(g))
+    return _workspace(device, stream_ptr, n)
 
 
 def _workspace(device: torch.device, stream_ptr: int, nbytes: int) -> torch.Tensor:
@@ -181,8 +206,8 @@ def energy_raw(geom: Geometry, u, nu=None, f=None, f_gp=None, dirichlet=(), nu_z
     loss64 = torch.empty((), dtype=torch.float64, device=dev) if want_double else None
     lib = L.lib()
     stream = torch.cuda.current_stream(dev).cuda_stream
-    with torch.cuda.device(dev):
-        ws = _workspace(dev, stream, lib.dn_fem_workspace_bytes(C.byref(g)))
+    with _on_device(dev):
+        ws = _workspace_for(lib, g, geom, B, dev, stream)
         fu, fnu, ff = _field(uc, B, geom.nsd), _field(nuc, B, geom.nsd), _field(fc, B, geom.nsd)
         ffg = L.dn_field(None, 0, 0, 0)
         if fg is not None:
@@ -213,8 +238,8 @@ def residual_raw(geom: Geometry, u, nu=None, f=None, dirichlet=(), jac=1.0, appl
     loss = _new_out((), dev)
     lib = L.lib()
     stream = torch.cuda.current_stream(dev).cuda_stream
-    with torch.cuda.device(dev):
-        ws = _workspace(dev, stream, lib.dn_fem_workspace_bytes(C.byref(g)))
+    with _on_device(dev):
+        ws = _workspace_for(lib, g, geom, B, dev, stream)
         fu, fnu, ff = _field(uc, B, geom.nsd), _field(nuc, B, geom.nsd), _field(fc, B, geom.nsd)
         fn = lib.dn_fem_residual_2d_f32 if geom.nsd == 2 else lib.dn_fem_residual_3d_f32
         rc = fn(C.byref(fu), C.byref(fnu) if nuc is not None else None,
@@ -231,7 +256,7 @@ def scale_inplace_(x: torch.Tensor, factor: torch.Tensor) -> torch.Tensor:
     assert x.is_contiguous() and x.dtype == torch.float32
     fac = factor.detach().to(device=x.device, dtype=torch.float32).reshape(())
     stream = torch.cuda.current_stream(x.device).cuda_stream
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         rc = L.lib().dn_scale_inplace_f32(C.c_void_p(x.data_ptr()), x.numel(),
                                           C.c_void_p(fac.data_ptr()), C.c_void_p(stream))
     L.check(rc, "dn_scale_inplace_f32")
@@ -318,7 +343,7 @@ def _gp_raw(geom: Geometry, t: torch.Tensor, which: int) -> torch.Tensor:
     stream = torch.cuda.current_stream(tc.device).cuda_stream
     lib = L.lib()
     fn = lib.dn_fem_gp_eval_2d_f32 if geom.nsd == 2 else lib.dn_fem_gp_eval_3d_f32
-    with torch.cuda.device(tc.device):
+    with _on_device(tc.device):
         rc = fn(C.byref(fld), C.byref(g), which, _ptr(out), C.c_void_p(stream))
     L.check(rc, "dn_fem_gp_eval")
     return out
@@ -341,7 +366,7 @@ class GaussPointEvalFunction(torch.autograd.Function):
         stream = torch.cuda.current_stream(gout.device).cuda_stream
         lib = L.lib()
         fn = lib.dn_fem_gp_eval_adj_2d_f32 if geom.nsd == 2 else lib.dn_fem_gp_eval_adj_3d_f32
-        with torch.cuda.device(gout.device):
+        with _on_device(gout.device):
             rc = fn(_ptr(gout), C.byref(g), ctx.which, _ptr(gin), C.c_void_p(stream))
         L.check(rc, "dn_fem_gp_eval_adj")
         return _like_input(gin, ctx.t_ref, geom), None, None
