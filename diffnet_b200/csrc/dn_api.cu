@@ -238,7 +238,7 @@ static Plan2T plan2t(const dn_geom* g, int nf, int sms, occ2t_fn occ) {
   return pl;
 }
 
-static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, void* workspace,
+static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, int mask_input, void* workspace,
                  size_t wsb, double* loss_out, float* loss_f32, void* stream, int sms, bool* handled) {
   *handled = false;
   const char* path = getenv("DN_2D_PATH");
@@ -246,8 +246,14 @@ static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, void*
   if (!c.vec4 || c.fgp.p || ((uintptr_t)grad % 16 != 0)) return DN_OK;
   const int NU = c.nu.p ? 1 : 0, F = c.f.p ? 1 : 0, NMK = c.numask.p ? 1 : 0;
   if (g->nx % 4 != 0 || g->nx / 4 > DN_T2_MAXT) return DN_OK;
-  launch2t_fn fn = get_launch2t(c.MK, NU, F, NMK);
-  occ2t_fn occ = get_occ2t(c.MK, NU, F, NMK);
+  int MKx = c.MK;
+  if (!mask_input) {                     // operator apply: only the plain-mask, no-source variants exist
+    if (c.MK == 0) MKx = 0;              // nothing to substitute anyway
+    else if (c.MK >= 1 && c.MK <= 3 && !F && !NMK) MKx = c.MK + 4;
+    else return DN_OK;
+  }
+  launch2t_fn fn = get_launch2t(MKx, NU, F, NMK);
+  occ2t_fn occ = get_occ2t(MKx, NU, F, NMK);
   if (!fn || !occ) return DN_OK;
   P2T p;
   memset(&p, 0, sizeof(p));
@@ -288,9 +294,9 @@ static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, void*
 static int run2d(const Common& c, const dn_geom* g, float* grad, float* grad_nu, int mode,
                  int mask_input, void* workspace, size_t wsb, double* loss_out, float* loss_f32,
                  void* stream, int sms) {
-  if (!grad_nu && mask_input) {   // streaming path: common aligned cases (the rest stays on k_fem2d)
+  if (!grad_nu) {   // streaming path: common aligned cases (the rest stays on k_fem2d)
     bool handled = false;
-    int rc = run2t(c, g, grad, mode, workspace, wsb, loss_out, loss_f32, stream, sms, &handled);
+    int rc = run2t(c, g, grad, mode, mask_input, workspace, wsb, loss_out, loss_f32, stream, sms, &handled);
     if (rc != DN_OK || handled) return rc;
   }
   bool vec4 = c.vec4 && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)grad_nu % 16 == 0);

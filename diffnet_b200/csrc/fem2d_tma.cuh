@@ -175,7 +175,7 @@ struct Acc2T {
   float a4;
 };
 
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI = true>
 struct Fem2T {
   static constexpr int NF = 1 + (HAS_NU ? 1 : 0) + (HAS_F ? 1 : 0) + (NUMASK ? 1 : 0) + NM + (VF ? 1 : 0);
   static constexpr int F_U = 0, F_NU = 1, F_F = F_NU + (HAS_NU ? 1 : 0), F_NM = F_F + (HAS_F ? 1 : 0),
@@ -201,7 +201,7 @@ struct Fem2T {
 #pragma unroll
       for (int m = 0; m < NM; ++m) {
         const bool hit = v[F_M + m][e] > 0.5f;
-        u = hit ? (VF ? v[F_VF][e] : p.mval[m]) : u;
+        if constexpr (MI) u = hit ? (VF ? v[F_VF][e] : p.mval[m]) : u;   // MI = false: operator apply, values not substituted
         fx = fx || hit;
       }
       ub[e] = u;
@@ -290,9 +290,9 @@ __device__ __forceinline__ void finish_loss_w0(const Reduce& r, double cta_value
 }
 
 // TB = max threads per CTA, MINB = min resident CTAs per SM the register allocation must allow.
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, int TB, int MINB>
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI, int TB, int MINB>
 __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ P2T p) {
-  using F = Fem2T<NM, VF, HAS_NU, HAS_F, NUMASK>;
+  using F = Fem2T<NM, VF, HAS_NU, HAS_F, NUMASK, MI>;
   constexpr int NF = F::NF;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[TB / 32];
@@ -466,8 +466,10 @@ constexpr int kMaxDynSmem = 226 * 1024;   // 227 KB per CTA minus the kernels' s
 // 256^2 x 64: more CTAs per wave means shorter row chunks and more seam work (profiles/).
 template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
 struct Kern2T {
-  static constexpr int NM = (MK == 4) ? 1 : MK;
-  static auto get() { return k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK, DN_T2_MAXT, 1>; }
+  // MK 0..3: that many scalar-valued masks; 4: one mask with a value field; 5..7: 1..3 masks whose
+  // values are NOT substituted into u (mask_input = 0: the operator v -> mask(K v) of the resmin backward)
+  static constexpr int NM = (MK == 4) ? 1 : (MK >= 5 ? MK - 4 : MK);
+  static auto get() { return k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK, (MK < 5), DN_T2_MAXT, 1>; }
 };
 
 template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>

@@ -84,7 +84,7 @@ __device__ __forceinline__ void dir_q(float2 d0, float2 d1, float2 d2, float2 d3
   q3 = fma2(d0, Q33, fma2(d1, Q2, fma2(d2, Q1, mul2(d3, P0))));
 }
 
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI = true>
 struct Fem3T {
   static constexpr int NF = 1 + (HAS_NU ? 1 : 0) + (HAS_F ? 1 : 0) + (NUMASK ? 1 : 0) + NM + (VF ? 1 : 0);
   static constexpr int F_U = 0, F_NU = 1, F_F = F_NU + (HAS_NU ? 1 : 0), F_NM = F_F + (HAS_F ? 1 : 0),
@@ -121,7 +121,7 @@ struct Fem3T {
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
           const bool hit = v[F_M + m][e] > 0.5f;
-          u = hit ? (VF ? v[F_VF][e] : p.mval[m]) : u;
+          if constexpr (MI) u = hit ? (VF ? v[F_VF][e] : p.mval[m]) : u;   // MI = false: operator apply
           fx = fx || hit;
         }
         ub[e] = u;
@@ -232,9 +232,9 @@ __device__ __forceinline__ RowG face_to_rows(const Face& g) {   // transposed y-
   return o;
 }
 
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI>
 __global__ void __launch_bounds__(DN_T3_MAXT_OF(HAS_NU), 1) k_fem3d_tma(const __grid_constant__ P3T p) {
-  using F = Fem3T<NM, VF, HAS_NU, HAS_F, NUMASK>;
+  using F = Fem3T<NM, VF, HAS_NU, HAS_F, NUMASK, MI>;
   constexpr int NF = F::NF;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[DN_T3_MAXT / 32];
@@ -422,8 +422,9 @@ occ3t_fn get_occ3t(int MK, int NU, int F, int NUMASK);
 
 template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
 struct Kern3T {
-  static constexpr int NM = (MK == 4) ? 1 : MK;
-  static auto get() { return k_fem3d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK>; }
+  // MK 0..3 / 4 / 5..7 as in fem2d_tma.cuh (5..7: mask_input = 0)
+  static constexpr int NM = (MK == 4) ? 1 : (MK >= 5 ? MK - 4 : MK);
+  static auto get() { return k_fem3d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK, (MK < 5)>; }
 };
 
 template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>

@@ -188,10 +188,16 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   *handled = false;
   const char* path = getenv("DN_3D_PATH");
   if (path && !strcmp(path, "tile")) return DN_OK;
-  if (!vec4 || fgp.p || !mask_input || ((uintptr_t)grad % 16 != 0)) return DN_OK;
+  if (!vec4 || fgp.p || ((uintptr_t)grad % 16 != 0)) return DN_OK;
   const int NU = nu.p ? 1 : 0, F = f.p ? 1 : 0, NMK = numask.p ? 1 : 0;
-  launch3t_fn fn = get_launch3t(MK, NU, F, NMK);
-  occ3t_fn occ = get_occ3t(MK, NU, F, NMK);
+  int MKx = MK;
+  if (!mask_input) {                     // operator apply: only the plain-mask, no-source variants exist
+    if (MK == 0) MKx = 0;
+    else if (MK >= 1 && MK <= 3 && !F && !NMK) MKx = MK + 4;
+    else return DN_OK;
+  }
+  launch3t_fn fn = get_launch3t(MKx, NU, F, NMK);
+  occ3t_fn occ = get_occ3t(MKx, NU, F, NMK);
   if (!fn || !occ || !get_encode()) return DN_OK;
   Field fl[DN_T2_MAXF];
   P3T p;

@@ -6,6 +6,10 @@ namespace dn {
 #define DN_INST(MK, NU, F, NMK)                                                                 \
   template cudaError_t launch3t<MK, NU, F, NMK>(const P3T&, dim3, dim3, size_t, cudaStream_t);  \
   template int occ3t<MK, NU, F, NMK>(int, size_t);
+#if DN_MK >= 5
+DN3T_COMBOS_OP(DN_INST, DN_MK)
+#else
 DN3T_COMBOS(DN_INST, DN_MK)
+#endif
 #undef DN_INST
 }  // namespace dn

@@ -334,6 +334,29 @@ def test_streaming_and_warp_paths_agree():
         assert torch.equal(gs == 0, gw == 0) or rel_l2(gs, gw) < 2e-6
 
 
+def test_residual_form_streaming_vs_general():
+    """sum(R^2) and its gradient (one more operator pass with mask_input = 0) on the streaming
+    kernels vs the general kernels."""
+    B, H, W = 2, 40, 136
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W)
+    u, inputs, f = make_inputs(B, H, W, seed=9)
+    u, inputs, f = u.to(DEV), inputs.to(DEV), f.to(DEV)
+    nu, bc1, bc2 = inputs[:, 0:1], inputs[:, 1:2], inputs[:, 2:3]
+    out = {}
+    for path in ("", "warp"):
+        if path:
+            os.environ["DN_2D_PATH"] = path
+        try:
+            ud = u.clone().requires_grad_(True)
+            loss = fem.residual_loss(ud, nu=nu, f=f, dirichlet=[(bc1, 1.0), (bc2, 0.0)], jac=(0.5 * fem.h) ** 2)
+            loss.backward()
+            out[path] = (loss.detach(), ud.grad.detach())
+        finally:
+            os.environ.pop("DN_2D_PATH", None)
+    assert rel_scalar(out[""][0], out["warp"][0]) < 2e-6
+    assert rel_l2(out[""][1], out["warp"][1]) < 2e-6
+
+
 def test_errors_are_loud():
     from diffnet_b200._lib import DiffNetFEMError
     fem = DiffNet2DFEM(None, domain_size=16)

@@ -190,6 +190,25 @@ def test_streaming_and_tile_paths_agree():
         assert rel_l2(gs, gw) < 2e-6, sorted(kw)
 
 
+def test_residual_form_streaming_vs_general():
+    B, D, H, W = 1, 11, 14, 40
+    fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_size=W)
+    u, nu, f, src, sink = (t.to(DEV) for t in make_inputs(B, D, H, W, seed=21))
+    out = {}
+    for path in ("", "tile"):
+        if path:
+            os.environ["DN_3D_PATH"] = path
+        try:
+            ud = u.clone().requires_grad_(True)
+            loss = fem.residual_loss(ud, nu=nu, f=f, dirichlet=[(sink, 0.0), (src, 1.0)], jac=(0.5 * fem.h) ** 3)
+            loss.backward()
+            out[path] = (loss.detach(), ud.grad.detach())
+        finally:
+            os.environ.pop("DN_3D_PATH", None)
+    assert rel_scalar(out[""][0], out["tile"][0]) < 2e-6
+    assert rel_l2(out[""][1], out["tile"][1]) < 2e-6
+
+
 def test_z_slab_ownership_matches_whole_domain():
     """slabs with one-plane halos, loss summed over owned layers, gradient complete
     on owned planes, divided by the GLOBAL element count -- emulated on one GPU."""
