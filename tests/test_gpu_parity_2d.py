@@ -305,6 +305,19 @@ def test_full_size_properties():
         assert torch.equal(g1[0], gs[3])
 
 
+@pytest.mark.parametrize("B,N", [(2, 256), (1, 512)])
+def test_baseline_grids_against_oracle(B, N):
+    """The BASELINE grids themselves (256^2, 512^2; small batch so the fp64 oracle finishes in
+    seconds) through the streaming kernel: loss <= 1e-5, gradient <= 1e-4, zeros on Dirichlet nodes."""
+    fem = DiffNet2DFEM(None, domain_size=N)
+    u, inputs, f = make_inputs(B, N, N, seed=N)
+    nu, bc1, bc2 = inputs[:, 0:1], inputs[:, 1:2], inputs[:, 2:3]
+    kw = dict(nu=nu, f=f, dirichlet=[(bc1, 1.0), (bc2, 0.0)])
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, masks=(bc1, bc2), what=f"E1 {B}x{N}x{N}")
+
+
 def test_streaming_and_warp_paths_agree():
     """The bulk-async streaming kernel (k_fem2d_tma) and the general warp-marching kernel
     (k_fem2d) are two implementations of the same operator: same loss, same gradient, on the

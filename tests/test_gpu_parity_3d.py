@@ -166,6 +166,18 @@ def test_full_size_properties():
             assert rel_scalar(lb, loss) < 2e-6 and rel_l2(gb, grad) < 2e-6, knobs
 
 
+@pytest.mark.parametrize("N", [64, 128])
+def test_baseline_grids_against_oracle(N):
+    """64^3 and 128^3 (B = 1 so the fp64 oracle finishes in seconds) through the streaming
+    kernel, full Poisson (u, nu, f, two masks)."""
+    fem = DiffNet3DFEM(None, domain_size=N)
+    u, nu, f, src, sink = make_inputs(1, N, N, N, seed=N)
+    kw = dict(nu=nu, f=f, dirichlet=[(sink, 0.0), (src, 1.0)])
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, masks=(src, sink), what=f"3D {N}^3")
+
+
 def test_streaming_and_tile_paths_agree():
     """k_fem3d_tma (bulk-async streaming) vs k_fem3d (general tile kernel): same operator."""
     B, D, H, W = 2, 19, 37, 72
