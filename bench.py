@@ -143,7 +143,7 @@ def call_kwargs(d):
 
 
 # ------------------------------------------------------------------------------------ oracle legs
-def oracle_step_time(name, sample_B, threads, repeats=3):
+def oracle_step_time(name, sample_B, threads, repeats=8):
     """fwd+bwd of the oracle (reference conv path restated) on the CPU; best of `repeats`."""
     import torch
     from oracle import losses as OL
@@ -389,11 +389,13 @@ def run_ours(args):
         e2e_step()
     Ke = max(3, min(K, 20))
     barrier()
-    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
     for _ in range(Ke):
-        e2e_step()
+        e2e_step()                                  # H2D copies + launch + loss.item() (a sync) every step
+    g1.record()
     torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    te = torch.tensor([g0.elapsed_time(g1) * 1e-3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = dof_step * world * Ke / float(te.item()) / 1e9
@@ -414,7 +416,7 @@ def run_ours(args):
             sB = cpu_sample_batch(name)
             best, dof = oracle_step_time(name, sB, threads)
             cpu = {"value": dof / best / 1e9, "unit": "GDOF/s", "cores": threads, "kind": "port",
-                   "sample": f"oracle fwd+bwd on B={sB} of {B} samples ({dof} DOF), best of 3, torch {torch.__version__} CPU"}
+                   "sample": f"oracle fwd+bwd on B={sB} of {B} samples ({dof} DOF), best of 8, torch {torch.__version__} CPU"}
             if name != "poisson3d_256_b1":      # the conv path materialises ~20 GB of Gauss-point tensors at 256^3
                 try:
                     tg, dg = oracle_on_gpu_time(name, dev)
@@ -441,7 +443,7 @@ def run_ours(args):
                          "kernel": "k_fem2d_tma" if nsd == 2 else "k_fem3d_tma"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": Ke, "note": "pinned host -> device copy of all input fields + fused launch + loss.item()"},
+                    "steps": Ke, "note": "pinned host -> device copy of all input fields + fused launch + loss.item() every step; CUDA events around the steps, max over ranks"},
             "gpu_launches": K,
             "clocks": clocks,
             "train": train,
