@@ -6,8 +6,8 @@ Importing the package does not load CUDA; the first op call loads
 """
 from .base import PDE
 from .fem import DiffNet2DFEM, DiffNet3DFEM, DiffNetFEM
-from .ops import (Geometry, fem_energy, fem_energy_and_grad, fem_residual, gp_eval)
+from .ops import (Geometry, PreparedEnergy, fem_energy, fem_energy_and_grad, fem_residual, gp_eval)
 
-__all__ = ["PDE", "DiffNetFEM", "DiffNet2DFEM", "DiffNet3DFEM", "Geometry", "fem_energy",
+__all__ = ["PDE", "DiffNetFEM", "DiffNet2DFEM", "DiffNet3DFEM", "Geometry", "PreparedEnergy", "fem_energy",
            "fem_energy_and_grad", "fem_residual", "gp_eval"]
 __version__ = "0.1.0"

@@ -161,6 +161,11 @@ class DiffNetFEM(PDE):
         """(loss, dloss/du) in one launch, outside autograd."""
         return ops.fem_energy_and_grad(self.geometry, u, **kw)
 
+    def prepare_energy(self, u, **kw):
+        """Bind a fused energy call to fixed tensors (see ops.PreparedEnergy): ``call = fem.prepare_energy(u,
+        nu=..., ...)``, then ``loss, grad = call()`` costs one C call per evaluation."""
+        return ops.PreparedEnergy(self.geometry, u, **kw)
+
     def residual_loss(self, u, nu=None, f=None, dirichlet=(), jac=1.0):
         """sum(R^2) of the assembled, Dirichlet-zeroed Galerkin residual (12_klsum.py:80-132)."""
         return ops.fem_residual(self.geometry, u, nu=nu, f=f, dirichlet=dirichlet, jac=jac)

@@ -72,8 +72,22 @@ def cut(t: torch.Tensor, slab: Slab, zdim: int = -3) -> torch.Tensor:
     return t.narrow(zdim, slab.lo, slab.hi - slab.lo).contiguous()
 
 
+_prepared = {}
+
+
 def _default_energy(geom, u, **kw):
-    loss, grad, _ = ops.energy_raw(geom, u, **kw)
+    """The CUDA op.  Slab steps call it on the same storage every iteration: the marshalled call
+    (ops.PreparedEnergy) is cached per (storage, shape, ownership)."""
+    key = (u.data_ptr(), tuple(u.shape), geom, kw.get("z_own"), kw.get("mean_count"),
+           tuple((m.data_ptr(), v.data_ptr() if torch.is_tensor(v) else v) for m, v in kw.get("dirichlet", ())),
+           tuple((k, v.data_ptr()) for k, v in kw.items() if torch.is_tensor(v)),
+           tuple((k, v) for k, v in kw.items() if isinstance(v, (int, float))))
+    call = _prepared.get(key)
+    if call is None:
+        if len(_prepared) > 64:
+            _prepared.clear()
+        call = _prepared[key] = ops.PreparedEnergy(geom, u, **kw)
+    loss, grad = call()
     return loss, grad
 
 

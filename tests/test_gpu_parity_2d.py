@@ -370,6 +370,24 @@ def test_residual_form_streaming_vs_general():
     assert rel_l2(out[""][1], out["warp"][1]) < 2e-6
 
 
+def test_prepared_call_equals_plain_call():
+    """ops.PreparedEnergy (marshalling done once) == energy_loss_and_grad, sees in-place updates of
+    the bound tensors, and reuses its output buffers."""
+    fem = DiffNet2DFEM(None, domain_size=64)
+    u, inputs, f = make_inputs(3, 64, 64, seed=2)
+    u, inputs, f = u.to(DEV), inputs.to(DEV), f.to(DEV)
+    kw = dict(nu=inputs[:, 0:1], f=f, dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)], c_k=0.5)
+    call = fem.prepare_energy(u, **kw)
+    l0, g0 = fem.energy_loss_and_grad(u, **kw)
+    l1, g1 = call()
+    assert torch.equal(l0, l1) and torch.equal(g0, g1)
+    u.mul_(1.5)
+    l2, g2 = fem.energy_loss_and_grad(u, **kw)
+    l3, g3 = call()
+    assert l3.data_ptr() == l1.data_ptr() and g3.data_ptr() == g1.data_ptr()
+    assert torch.equal(l2, l3) and torch.equal(g2, g3)
+
+
 def test_errors_are_loud():
     from diffnet_b200._lib import DiffNetFEMError
     fem = DiffNet2DFEM(None, domain_size=16)
