@@ -35,6 +35,7 @@ WORKLOADS = {
     "poisson2d_param_256_b256": (2, 256, 256, 24, "scaling probe: 256x256, batch 256"),
     "poisson2d_param_256_b1024": (2, 256, 1024, 24, "scaling probe: 256x256, batch 1024"),
     "poisson2d_512_b16": (2, 512, 16, 24, "Poisson 2D 512x512 Q1, batch 16/GPU (roofline point)"),
+    "poisson2d_512_b1": (2, 512, 1, 24, "Poisson 2D 512x512, batch 1 (IBN 2D single image; latency probe)"),
     "poisson2d_64_b1": (2, 64, 1, 24, "Poisson 2D non-parametric 64x64 (configs[0])"),
     "poisson3d_param_64_b16": (3, 64, 16, 20, "Poisson 3D parametric 64^3 Q1 hex, batch 16/GPU (u, source, sink, f)"),
     "poisson3d_128_b1": (3, 128, 1, 24, "Poisson 3D 128^3, variable nu, f, two masks (roofline point)"),
