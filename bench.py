@@ -35,6 +35,7 @@ WORKLOADS = {
     "poisson2d_param_256_b256": (2, 256, 256, 24, "scaling probe: 256x256, batch 256"),
     "poisson2d_param_256_b1024": (2, 256, 1024, 24, "scaling probe: 256x256, batch 1024"),
     "poisson2d_512_b16": (2, 512, 16, 24, "Poisson 2D 512x512 Q1, batch 16/GPU (roofline point)"),
+    "ibn2d_512_b16": (2, 512, 16, 24, "IBN 2D irregular-domain Poisson, synthetic immersed silhouettes, 512x512, batch 16/GPU (configs[4])"),
     "poisson2d_512_b1": (2, 512, 1, 24, "Poisson 2D 512x512, batch 1 (IBN 2D single image; latency probe)"),
     "poisson2d_64_b1": (2, 64, 1, 24, "Poisson 2D non-parametric 64x64 (configs[0])"),
     "poisson3d_param_64_b16": (3, 64, 16, 20, "Poisson 3D parametric 64^3 Q1 hex, batch 16/GPU (u, source, sink, f)"),
@@ -117,10 +118,11 @@ class ClockSampler:
 
 def make_inputs(name, device, seed):
     import torch
-    from diffnet_b200.synthetic import poisson2d_parametric_batch, poisson3d_parametric_batch
+    from diffnet_b200.synthetic import ibn2d_batch, poisson2d_parametric_batch, poisson3d_parametric_batch
     nsd, size, B, _, _ = WORKLOADS[name]
     if nsd == 2:
-        u, inputs, f = poisson2d_parametric_batch(B, size, device, seed)
+        gen = ibn2d_batch if name.startswith("ibn2d") else poisson2d_parametric_batch
+        u, inputs, f = gen(B, size, device, seed)
         return dict(u=u, nu=inputs[:, 0:1], f=f, dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)],
                     _fields=[u, inputs, f])
     u, src, sink, f = poisson3d_parametric_batch(B, size, device, seed)

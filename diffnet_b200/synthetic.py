@@ -6,6 +6,9 @@ Not on the hot path.  Recipes restated from the reference:
     examples/poisson/parametric/sobol_6d.npy).  The frequencies omega_i are the roots of
     (eta^2 w^2 - 1) sin w = 2 eta w cos w, found here by bisection instead of a constant table.
   * bc1 = first column, bc2 = last column (DiffNet/datasets/parametric/klsum.py:24-32).
+  * immersed-geometry image inputs [domain, bc1 = object, bc2 = the four edges]
+    (DiffNet/datasets/parametric/images.py:9-49, ImageIMBack) with star-shaped random silhouettes
+    standing in for the 1464 PNGs of IBN/datasets/imagedataset.tar.gz.
   * 3-D source/sink masks: union of random boxes as "source", the six faces as "sink"
     (IBN/poisson-3d/parametric/IBN_3D.py:76-104).
 """
@@ -58,6 +61,32 @@ def poisson2d_parametric_batch(B: int, size: int, device, seed: int = 1234):
     bc1 = torch.zeros(B, 1, size, size, device=device); bc1[..., 0] = 1
     bc2 = torch.zeros(B, 1, size, size, device=device); bc2[..., -1] = 1
     inputs = torch.cat([nu, bc1, bc2], 1).contiguous()
+    forcing = torch.zeros(B, 1, size, size, device=device)
+    u = (torch.randn(B, 1, size, size, generator=g) * 0.5 + 0.5).to(device)
+    return u, inputs, forcing
+
+
+def ibn2d_batch(B: int, size: int, device, seed: int = 1234):
+    """(u, inputs (B,3,H,W) = [domain, bc1, bc2], forcing) like ImageIMBack: a random star-shaped
+    object per sample (radius r(theta) = r0 (1 + sum_k a_k cos(k theta + p_k))), domain = 1 outside
+    it, bc1 = the object (u -> 1), bc2 = the four edges (u -> 0)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    y, x = torch.meshgrid(torch.linspace(-1, 1, size), torch.linspace(-1, 1, size), indexing="ij")
+    obj = torch.zeros(B, 1, size, size)
+    for b in range(B):
+        c = (torch.rand(2, generator=g) - 0.5) * 0.6
+        r0 = 0.25 + 0.2 * float(torch.rand(1, generator=g))
+        th = torch.atan2(y - c[1], x - c[0])
+        rad = torch.full_like(th, r0)
+        for k in range(2, 6):
+            a = 0.25 * float(torch.rand(1, generator=g)) / k
+            ph = 6.2831853 * float(torch.rand(1, generator=g))
+            rad = rad + r0 * a * torch.cos(k * th + ph)
+        obj[b, 0] = (torch.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2) < rad).float()
+    domain = 1.0 - obj
+    bc2 = torch.zeros(B, 1, size, size)
+    bc2[..., 0] = 1; bc2[..., -1] = 1; bc2[:, :, 0, :] = 1; bc2[:, :, -1, :] = 1
+    inputs = torch.cat([domain, obj, bc2], 1).contiguous().to(device)
     forcing = torch.zeros(B, 1, size, size, device=device)
     u = (torch.randn(B, 1, size, size, generator=g) * 0.5 + 0.5).to(device)
     return u, inputs, forcing

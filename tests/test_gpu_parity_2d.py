@@ -318,6 +318,23 @@ def test_baseline_grids_against_oracle(B, N):
     assert_parity(loss, grad, lref, gref, masks=(bc1, bc2), what=f"E1 {B}x{N}x{N}")
 
 
+def test_immersed_geometry_masks():
+    """configs[4]: IBN 2-D with irregular (star-shaped) object masks, nu = domain indicator
+    (0 inside the object), bc1 = object, bc2 = the four edges -- overlapping masks on the corners and
+    wherever a silhouette touches an edge (e1_complex_immersed_background.py:33-58)."""
+    from diffnet_b200.synthetic import ibn2d_batch
+    B, N = 3, 128
+    fem = DiffNet2DFEM(None, domain_size=N)
+    u, inputs, f = ibn2d_batch(B, N, torch.device("cpu"), seed=3)
+    f = torch.randn_like(f)
+    nu, bc1, bc2 = inputs[:, 0:1], inputs[:, 1:2], inputs[:, 2:3]
+    assert 0.02 < float(bc1.mean()) < 0.6
+    kw = dict(nu=nu, f=f, dirichlet=[(bc1, 1.0), (bc2, 0.0)])
+    loss, grad = run_energy(fem, u, **kw)
+    lref, gref = oracle_energy(fem, u, **kw)
+    assert_parity(loss, grad, lref, gref, masks=(bc1, bc2), what="IBN 2-D silhouettes")
+
+
 def test_streaming_and_warp_paths_agree():
     """The bulk-async streaming kernel (k_fem2d_tma) and the general warp-marching kernel
     (k_fem2d) are two implementations of the same operator: same loss, same gradient, on the
