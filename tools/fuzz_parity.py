@@ -23,12 +23,12 @@ def rel(a, b):
 def case(i):
     nsd = rng.choice([2, 2, 3])
     if nsd == 2:
-        nx = rng.choice([8, 12, 36, 64, 100, 132, 256, 260, 516]); ny = rng.randint(2, 70)
+        nx = rng.choice([8, 12, 36, 64, 100, 132, 256, 260, 516, 1024, 2048, 2052]); ny = rng.randint(2, 70)
         sizes, dims = (nx, ny, 1), (ny, nx)
     else:
-        nx = rng.choice([8, 12, 20, 36, 64, 72, 132]); ny = rng.randint(2, 24); nz = rng.randint(2, 20)
+        nx = rng.choice([8, 12, 20, 36, 64, 72, 132, 256, 260, 516]); ny = rng.randint(2, 40); nz = rng.randint(2, 24)
         sizes, dims = (nx, ny, nz), (nz, ny, nx)
-    B = rng.choice([1, 1, 2, 3, 5])
+    B = rng.choice([1, 1, 2, 3, 5, 17])
     lengths = (1.0, rng.choice([1.0, 0.7]), rng.choice([1.0, 0.4]))
     cls = DiffNet2DFEM if nsd == 2 else DiffNet3DFEM
     fem = cls(None, domain_sizes=sizes, domain_lengths=lengths, domain_size=nx)
