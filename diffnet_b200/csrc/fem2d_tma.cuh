@@ -144,11 +144,10 @@ __device__ __forceinline__ float2 elem_pair(const K2& k, float2 st, float2 dt, f
   float2 E, g0, gx, ge, gxe;
   if constexpr (HAS_F) {
     const float2 A0 = add2(st, sb);
-    const float2 nb0 = mul2(k.nkf, add2(fst, fsb));        // -kf B0
-    const float2 nbx = mul2(k.nkft, add2(fdt, fdb));       // -kf t Bxi
-    const float2 nbe = mul2(k.nkft, sub2(fsb, fst));       // -kf t Beta
-    const float2 nbxe = mul2(k.nkftt, sub2(fdb, fdt));     // -kf t^2 Bxieta
-    const float2 tx = add2(qx, nbx), te = add2(qe, nbe), txe = add2(qxe, nbxe);
+    const float2 nb0 = mul2(k.nkf, add2(fst, fsb));                    // -kf B0
+    const float2 tx = fma2(k.nkft, add2(fdt, fdb), qx);                // q - kf t Bxi
+    const float2 te = fma2(k.nkft, sub2(fsb, fst), qe);                // q - kf t Beta
+    const float2 txe = fma2(k.nkftt, sub2(fdb, fdt), qxe);             // q - kf t^2 Bxieta
     E = fma2(A0, nb0, fma2(Ax, tx, fma2(Ae, te, mul2(Axe, txe))));
     g0 = nb0; gx = add2(qx, tx); ge = add2(qe, te); gxe = add2(qxe, txe);
     const float2 m0 = sub2(g0, ge), m1 = add2(g0, ge), n0 = sub2(gx, gxe), n1 = add2(gx, gxe);

@@ -196,15 +196,13 @@ struct Fem3T {
     float2 E, g0, g1, g2, g3, g4, g5, g6, g7;
     if constexpr (HAS_F) {
       const float2 u0 = add2(Lu.m0, Uu.m0);
-      // nb_m = -kf t^order(m) f_m
+      // t_m = q_m + nb_m with nb_m = -kf t^order(m) f_m, fused: one FFMA2 per mode
       const float2 nb0 = mul2(k.nkf, add2(Lf.m0, Uf.m0));
-      const float2 nb1 = mul2(k.nkft, add2(Lf.m1, Uf.m1)), nb2 = mul2(k.nkft, add2(Lf.m2, Uf.m2)),
-                   nb4 = mul2(k.nkft, sub2(Uf.m0, Lf.m0));
-      const float2 nb3 = mul2(k.nkftt, add2(Lf.m3, Uf.m3)), nb5 = mul2(k.nkftt, sub2(Uf.m1, Lf.m1)),
-                   nb6 = mul2(k.nkftt, sub2(Uf.m2, Lf.m2));
-      const float2 nb7 = mul2(k.nkfttt, sub2(Uf.m3, Lf.m3));
-      const float2 t1 = add2(q1, nb1), t2 = add2(q2, nb2), t3 = add2(q3, nb3), t4 = add2(q4, nb4),
-                   t5 = add2(q5, nb5), t6 = add2(q6, nb6), t7 = add2(q7, nb7);
+      const float2 t1 = fma2(k.nkft, add2(Lf.m1, Uf.m1), q1), t2 = fma2(k.nkft, add2(Lf.m2, Uf.m2), q2),
+                   t4 = fma2(k.nkft, sub2(Uf.m0, Lf.m0), q4);
+      const float2 t3 = fma2(k.nkftt, add2(Lf.m3, Uf.m3), q3), t5 = fma2(k.nkftt, sub2(Uf.m1, Lf.m1), q5),
+                   t6 = fma2(k.nkftt, sub2(Uf.m2, Lf.m2), q6);
+      const float2 t7 = fma2(k.nkfttt, sub2(Uf.m3, Lf.m3), q7);
       E = fma2(u0, nb0, fma2(u1, t1, fma2(u2, t2, fma2(u3, t3, fma2(u4, t4, fma2(u5, t5, fma2(u6, t6,
                mul2(u7, t7))))))));
       g0 = nb0; g1 = add2(q1, t1); g2 = add2(q2, t2); g3 = add2(q3, t3); g4 = add2(q4, t4);
