@@ -139,9 +139,9 @@ def test_unfused_body_on_gp_eval_ops():
 
 
 def test_full_size_properties():
-    """64^3 B=16 and 128^3 B=1 (BASELINE sizes): Euler identity, constants, scaling, determinism,
+    """64^3 B=16, 128^3 and 256^3 B=1 (BASELINE sizes): Euler identity, constants, scaling, determinism,
     independence of the z-chunking / tile shape."""
-    for B, N in ((16, 64), (1, 128)):
+    for B, N in ((16, 64), (1, 128), (1, 256)):
         fem = DiffNet3DFEM(None, domain_size=N)
         g = torch.Generator(device=DEV).manual_seed(N)
         u = torch.randn(B, 1, N, N, N, device=DEV, generator=g)
