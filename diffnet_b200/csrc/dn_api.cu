@@ -228,6 +228,11 @@ static Plan2T plan2t(const dn_geom* g, int nf, int sms, occ2t_fn occ) {
   int Rmin = env_int("DN_T2_RMIN", 8);
   if (Rmin < 4) Rmin = 4;
   if (R < Rmin) R = Rmin;
+  // with more work than one wave, long chunks stop paying: 32-row chunks in several waves measured
+  // 0.85 (B = 256) and 0.96 (B = 1024) of the HBM peak against 0.77 / 0.93 for one wave of 64- /
+  // 256-row chunks (fewer, longer-lived CTAs expose every ring refill)
+  const int Rmax = env_int("DN_T2_RMAX", 32);
+  if (R > Rmax && Rmax >= Rmin) R = Rmax;
   R = env_int("DN_T2_R", R);
   if (R < 4) R = 4;
   if (R > g->ny) R = g->ny;
