@@ -405,6 +405,44 @@ def test_prepared_call_equals_plain_call():
     assert torch.equal(l2, l3) and torch.equal(g2, g3)
 
 
+def test_concurrent_streams_and_graph_replay():
+    """Two CUDA streams issue launches concurrently (one workspace per stream), and a captured
+    graph of several launches replays to the same bits as eager execution."""
+    fem = DiffNet2DFEM(None, domain_size=128)
+    u, inputs, f = make_inputs(8, 128, 128, seed=4)
+    u, inputs, f = u.to(DEV), inputs.to(DEV), f.to(DEV)
+    kw = dict(nu=inputs[:, 0:1], f=f, dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)])
+    lref, gref = fem.energy_loss_and_grad(u, **kw)
+    u2 = 2.0 * u
+    lref2, gref2 = fem.energy_loss_and_grad(u2, **kw)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs1, outs2 = [], []
+    for _ in range(20):
+        with torch.cuda.stream(s1):
+            outs1.append(fem.energy_loss_and_grad(u, **kw))
+        with torch.cuda.stream(s2):
+            outs2.append(fem.energy_loss_and_grad(u2, **kw))
+    torch.cuda.synchronize()
+    for (l, g), (l2, g2) in zip(outs1, outs2):
+        assert torch.equal(l, lref) and torch.equal(g, gref)
+        assert torch.equal(l2, lref2) and torch.equal(g2, gref2)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fem.energy_loss_and_grad(u, **kw)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        captured = [fem.energy_loss_and_grad(u if i % 2 == 0 else u2, **kw) for i in range(6)]
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    for i, (l, g) in enumerate(captured):
+        assert torch.equal(l, lref if i % 2 == 0 else lref2) and torch.equal(g, gref if i % 2 == 0 else gref2)
+
+
 def test_errors_are_loud():
     from diffnet_b200._lib import DiffNetFEMError
     fem = DiffNet2DFEM(None, domain_size=16)
