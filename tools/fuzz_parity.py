@@ -52,6 +52,8 @@ def case(i):
     if rng.random() < 0.2: kw["scale"] = 0.37
     if rng.random() < 0.2: kw["reduction"] = "sum"
     dev = lambda t: t.to(DEV)
+    if rng.random() < 0.15:
+        return residual_case(i, fem, nsd, sizes, B, u, kw, dev)
     kwd = {k: (dev(v) if torch.is_tensor(v) else ([(dev(m), val) for m, val in v] if k == "dirichlet" else v)) for k, v in kw.items()}
     ud = dev(u)
     ls, gs = fem.energy_loss_and_grad(ud, **kwd)
@@ -78,6 +80,33 @@ def case(i):
         assert el2 < 1e-5 and eg2 < 1e-4, f"{desc}: vs oracle loss {el2:.2e} grad {eg2:.2e}"
         for m, _ in kw.get("dirichlet", ()):
             assert float((gs.reshape(gref.shape).cpu() * (m > 0.5)).abs().max()) == 0.0, desc + " (gradient on a Dirichlet node)"
+    return desc
+
+
+def residual_case(i, fem, nsd, sizes, B, u, kw, dev):
+    """sum(R^2) and its gradient (a second operator pass with mask_input = 0): streaming vs general."""
+    rkw = {k: v for k, v in kw.items() if k in ("nu", "f", "dirichlet")}
+    rkwd = {k: (dev(v) if torch.is_tensor(v) else [(dev(m), val) for m, val in v]) for k, v in rkw.items()}
+    jac = (0.5 * fem.h) ** nsd
+    out = []
+    key = "DN_2D_PATH" if nsd == 2 else "DN_3D_PATH"
+    for path in (None, "warp" if nsd == 2 else "tile"):
+        if path:
+            os.environ[key] = path
+        try:
+            ud = dev(u).clone().requires_grad_(True)
+            loss = fem.residual_loss(ud, jac=jac, **rkwd)
+            loss.backward()
+            out.append((loss.detach(), ud.grad.detach()))
+        finally:
+            os.environ.pop(key, None)
+    torch.cuda.synchronize()
+    desc = f"case {i} (residual): nsd={nsd} sizes={sizes} B={B} opts={sorted(rkw)}"
+    (l0, g0), (l1, g1) = out
+    assert torch.isfinite(g0).all(), desc
+    el = abs(float(l0) - float(l1)) / max(abs(float(l1)), 1e-30)
+    eg = rel(g0, g1) if float(g1.norm()) > 0 else float(g0.abs().max())
+    assert el < 1e-5 and eg < 1e-5, f"{desc}: loss {el:.2e} grad {eg:.2e}"
     return desc
 
 
