@@ -32,9 +32,12 @@
 namespace dn {
 
 #define DN_T3_MAXT 640      // largest CTA of any variant
-// nu == 1 variants fit 96 registers without spills: 640-thread CTAs (20 warps/SM, +4 % measured);
-// variable-nu variants keep 512 threads x 128 registers (96 registers spill: -4 %)
+// Register budgets (__maxnreg__; one CTA per SM).  Registers are granted per warp in units of 1024
+// (measured: 112 registers/thread admit no more warps than 128), so the useful budgets are 96 and
+// 128: nu == 1 variants fit 96 without spills -> 640-thread CTAs (20 warps/SM, +4 % measured);
+// variable-nu variants need 128 -> 512-thread CTAs (96 registers spill: -4 %)
 #define DN_T3_MAXT_OF(HAS_NU) ((HAS_NU) ? 512 : 640)
+#define DN_T3_REGS_OF(HAS_NU) ((HAS_NU) ? 128 : 96)
 
 // pair-replicated constants (half-gradient convention: k, not 2k)
 struct K3 {
@@ -231,7 +234,7 @@ __device__ __forceinline__ RowG face_to_rows(const Face& g) {   // transposed y-
 }
 
 template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI>
-__global__ void __launch_bounds__(DN_T3_MAXT_OF(HAS_NU), 1) k_fem3d_tma(const __grid_constant__ P3T p) {
+__global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_constant__ P3T p) {
   using F = Fem3T<NM, VF, HAS_NU, HAS_F, NUMASK, MI>;
   constexpr int NF = F::NF;
   extern __shared__ __align__(128) unsigned char smem_raw[];

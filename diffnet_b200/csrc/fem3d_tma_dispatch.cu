@@ -139,6 +139,9 @@ static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_v
       const size_t smem = smem_3t(S, nf, fstride, threads);
       if (smem > (size_t)kMaxDynSmem) continue;
       int cps = occ ? occ(threads, smem) : (int)(65536 / (threads * 128));
+      if (env_i3("DN_DEBUG_PLAN", 0) >= 2)
+        fprintf(stderr, "[plan3t] candidate LXT=%d rows=%d TY=%d threads=%d smem=%zu -> %d CTA/SM\n", LXT, rows, TY,
+                threads, smem, cps);
       if (cps < 1) continue;
       const long long tiles = (long long)g->batch * nty * ntx;
       const int nzc_max = zc_forced > 0 ? 1 : (g->nz + zmin - 1) / zmin;
