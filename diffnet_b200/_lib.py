@@ -53,6 +53,7 @@ PROTOTYPES = {
     "dn_last_error": (C.c_char_p, []),
     "dn_device_check": (C.c_int, []),
     "dn_fem_workspace_bytes": (C.c_size_t, [_P(dn_geom)]),
+    "dn_debug_plan": (C.c_int, [_P(dn_geom), C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "dn_fem_energy_2d_f32": (C.c_int, _ENERGY_ARGS),
     "dn_fem_energy_3d_f32": (C.c_int, _ENERGY_ARGS),
     "dn_fem_residual_2d_f32": (C.c_int, _RESID_ARGS),

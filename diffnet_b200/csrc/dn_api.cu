@@ -12,6 +12,7 @@
 #include "gp_eval.cuh"
 
 namespace dn {
+int debug_plan3t(const dn_geom* g, int nfields, int has_nu, int64_t* out);
 cudaError_t launch_peer_put(float* dst_peer, const float* src, size_t n, int* remote_flag, int* local_counter,
                             unsigned int* ticket, cudaStream_t s);
 cudaError_t launch_peer_wait(float* halo, const float* staged, size_t n, const int* flag, int* expect,
@@ -355,6 +356,23 @@ size_t dn_fem_workspace_bytes(const dn_geom* g) {
     worst = plan3d_max_ctas(g);
   }
   return ws_bytes_for_grid(worst + 1024);
+}
+
+int dn_debug_plan(const dn_geom* g, int nfields, int has_nu, int64_t out[16]) {
+  if (!g || !out) return fail(DN_EINVAL, "NULL pointer");
+  for (int i = 0; i < 16; ++i) out[i] = 0;
+  if (nfields < 1 || nfields > DN_T2_MAXF) return fail(DN_EINVAL, "nfields=%d", nfields);
+  if (g->nsd == 2) {
+    Plan2T pl = plan2t(g, nfields, 148, nullptr);
+    out[0] = pl.ok;
+    if (pl.ok) {
+      out[1] = pl.threads; out[2] = pl.grid; out[3] = (int64_t)pl.smem; out[4] = pl.S;
+      out[5] = pl.R; out[6] = pl.nchunks;
+    }
+    return DN_OK;
+  }
+  if (g->nsd == 3) return debug_plan3t(g, nfields, has_nu, out);
+  return fail(DN_EINVAL, "nsd=%d", g->nsd);
 }
 
 int dn_fem_energy_2d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,

@@ -138,7 +138,7 @@ static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_v
       while (S > 2 && smem_3t(S, nf, fstride, threads) > (size_t)kMaxDynSmem) --S;
       const size_t smem = smem_3t(S, nf, fstride, threads);
       if (smem > (size_t)kMaxDynSmem) continue;
-      int cps = occ ? occ(threads, smem) : (int)(65536 / (threads * 128));
+      int cps = occ ? occ(threads, smem) : (int)(65536 / (threads * (maxt_variant > 512 ? 96 : 128)));
       if (env_i3("DN_DEBUG_PLAN", 0) >= 2)
         fprintf(stderr, "[plan3t] candidate LXT=%d rows=%d TY=%d threads=%d smem=%zu -> %d CTA/SM\n", LXT, rows, TY,
                 threads, smem, cps);
@@ -182,6 +182,17 @@ long long plan3t_max_ctas(const dn_geom* g) {
   long long n = (long long)g->batch * ntx * nty * nzc;
   const long long cap = 1LL << 22;
   return n < cap ? n : cap;
+}
+
+int debug_plan3t(const dn_geom* g, int nfields, int has_nu, int64_t* out) {
+  Plan3T pl = plan3t(g, nfields, 148, nullptr, DN_T3_MAXT_OF(has_nu));
+  out[0] = pl.ok;
+  if (pl.ok) {
+    out[1] = pl.threads; out[2] = pl.grid; out[3] = (int64_t)pl.smem; out[4] = pl.S;
+    out[5] = pl.TY; out[6] = pl.nty; out[7] = pl.LXT; out[8] = pl.ntx; out[9] = pl.ZC; out[10] = pl.nzc;
+    out[11] = pl.BX; out[12] = pl.BY; out[13] = pl.rows; out[14] = pl.LXo; out[15] = pl.hl;
+  }
+  return DN_OK;
 }
 
 int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, const Field& numask,

@@ -109,6 +109,14 @@ int dn_device_check(void);
 
 size_t dn_fem_workspace_bytes(const dn_geom* g);
 
+/* Launch shape the streaming planners pick for `g` with `nfields` input fields (u, nu, f, masks ...),
+ * using the static register bound instead of a device occupancy query, so it runs WITHOUT a GPU
+ * (tests of the planners).  out[0] = 1 if the streaming path is eligible by shape, then
+ * out[1..] = {threads per CTA, grid, dynamic shared memory bytes, ring stages,
+ *             2-D: rows per chunk R, chunks per image | 3-D: owned rows per tile TY, y tiles,
+ *             lanes per tile row LXT, x tiles, planes per chunk ZC, z chunks, box BX, box BY}. */
+int dn_debug_plan(const dn_geom* g, int nfields, int has_nu, int64_t out[16]);
+
 /*
  * Fused energy loss + gradient.
  *   loss = S * sum_{b,e} sum_g w_g ( c_k nu_g |grad u'|_g^2 - c_f u'_g f_g ),  S = scale / count
