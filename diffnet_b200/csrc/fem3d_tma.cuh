@@ -102,33 +102,36 @@ struct Fem3T {
   // Read node rows a (local row r) and b (r+1) of one plane from its ring stage, apply the
   // Dirichlet conditions / nu mask, and reduce to the face modes of u, nu, f.
   // `sp` points at (row r, column x0) of field 0; `fstride` floats between fields.
-  static __device__ __forceinline__ void load_faces(const P3T& p, const float* __restrict__ sp, int nx,
-                                                    int fstride, bool has_right, Face& Uu, Face& Un,
-                                                    Face& Uf, float2& keep_a, float2& keep_b) {
+  // `edge_warp` / `any_b` are warp-uniform: the phantom last element of a row / the domain's last
+  // node row live in this warp (the common warps skip that work with one branch).
+  static __device__ __forceinline__ void load_faces(const P3T& p, const float* __restrict__ sp, int BX,
+                                                    int fstride, bool has_right, bool edge_warp, bool any_b,
+                                                    Face& Uu, Face& Un, Face& Uf, float2& keep_a,
+                                                    float2& keep_b) {
     float2 su[2], du[2], sn[2], dn_[2], sf[2], df[2];
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
       float v[NF][3];
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
-        const float* q = sp + f * fstride + row * nx;
+        const float* q = sp + f * fstride + row * BX;
         const float2 t = *reinterpret_cast<const float2*>(q);
         v[f][0] = t.x; v[f][1] = t.y;
         v[f][2] = q[2];                // beyond the last node the TMA unit has written zeros
       }
-      float ub[3], nb[3], fb[3], kp[2];
+      float ub[3], nb[3], fb[3];
+      bool fx[3];
 #pragma unroll
       for (int e = 0; e < 3; ++e) {
         float u = v[F_U][e];
-        bool fx = false;
+        fx[e] = false;
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
           const bool hit = v[F_M + m][e] > 0.5f;
           if constexpr (MI) u = hit ? (VF ? v[F_VF][e] : p.mval[m]) : u;   // MI = false: operator apply
-          fx = fx || hit;
+          fx[e] = fx[e] || hit;
         }
         ub[e] = u;
-        if (e < 2) kp[e] = fx ? 0.f : 1.f;
         if constexpr (HAS_NU) {
           float n = v[F_NU][e];
           if constexpr (NUMASK) n = (v[F_NM][e] > 0.5f) ? 0.f : n;
@@ -136,17 +139,21 @@ struct Fem3T {
         }
         if constexpr (HAS_F) fb[e] = v[F_F][e];
       }
-      if (row == 0) keep_a = f2(kp[0], kp[1]); else keep_b = f2(kp[0], kp[1]);
+      if (row == 0) keep_a = f2(fx[0] ? 0.f : 1.f, fx[1] ? 0.f : 1.f);
+      else if (any_b) keep_b = f2(fx[0] ? 0.f : 1.f, fx[1] ? 0.f : 1.f);
       xs(ub, su[row], du[row]);
-      // the last element of a row does not exist: E and g are linear in (nu, f), so zeroing
-      // their x-sums/differences removes it (nu == 1 uses the weight vw instead)
-      if constexpr (HAS_NU) {
-        xs(nb, sn[row], dn_[row]);
-        if (!has_right) { sn[row].y = 0.f; dn_[row].y = 0.f; }
-      }
-      if constexpr (HAS_F) {
-        xs(fb, sf[row], df[row]);
-        if (!has_right) { sf[row].y = 0.f; df[row].y = 0.f; }
+      if constexpr (HAS_NU) xs(nb, sn[row], dn_[row]);
+      if constexpr (HAS_F) xs(fb, sf[row], df[row]);
+    }
+    // the last element of a row does not exist: E and g are linear in (nu, f), so zeroing
+    // their x-sums/differences removes it (nu == 1 uses the weight vw instead)
+    if (edge_warp) {
+      if (!has_right) {
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+          if constexpr (HAS_NU) { sn[row].y = 0.f; dn_[row].y = 0.f; }
+          if constexpr (HAS_F) { sf[row].y = 0.f; df[row].y = 0.f; }
+        }
       }
     }
     Uu.m0 = add2(su[0], su[1]); Uu.m1 = add2(du[0], du[1]);
@@ -233,6 +240,22 @@ __device__ __forceinline__ RowG face_to_rows(const Face& g) {   // transposed y-
   return o;
 }
 
+// One lane of the warp, chosen by the hardware (the branch around it must be warp-uniform).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
+// Exchange area of one parity (floats): [nb: 2 (NT + LXT)] [hb: XL] [ha: XL], XL = NT + LXT + 4.
+//   nb  row-b partial sums (float2 per thread), shifted by one tile row so that row 0 reads a
+//       permanently zero prefix;
+//   hb / ha  right-neighbour shares of row b / row a, shifted by one tile row + one lane.  The last
+//       lane of every tile row (its right neighbour belongs to another tile or does not exist) and
+//       lanes that hold no pair store to the trash word at the end of each array, so the slot a
+//       first lane reads stays zero: no predicates in the gather.
+__host__ __device__ __forceinline__ int xbuf_floats(int NT, int LXT) { return 4 * NT + 4 * LXT + 8; }
+
 template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI>
 __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_constant__ P3T p) {
   using F = Fem3T<NM, VF, HAS_NU, HAS_F, NUMASK, MI>;
@@ -240,13 +263,15 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[DN_T3_MAXT / 32];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const int nx = p.nx, LXT = p.LXT, S = p.S;
-  const int NT = blockDim.x;                             // >= LXT * rows, multiple of 32
-  const int BX = p.BX, fstride = p.fstride, stage_floats = NF * fstride;
-  float* ring = reinterpret_cast<float*>(smem_raw);                                   // [S][NF][fstride]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats);      // [S]
-  float* xbuf = reinterpret_cast<float*>(full + S);                                   // [2][4][NT]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction
+  const int NT = blockDim.x;                                // >= LXT * rows, multiple of 32
+  const int nx = p.nx, LXT = p.LXT, S = p.S, BX = p.BX, fstride = p.fstride;
+  const int stage_floats = NF * fstride;
+  float* const ring = reinterpret_cast<float*>(smem_raw);                                   // [S][NF][fstride]
+  uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats);      // [S]
+  float* const xbuf = reinterpret_cast<float*>(full + S);                                   // [2][xbuf_floats]
+  const int XL = NT + LXT + 4, HB = 2 * (NT + LXT), HA = HB + XL, XB = HA + XL;
 
   // ---- work item: (b, z-chunk, y-tile, x-tile)
   int w_ = blockIdx.x;
@@ -265,10 +290,10 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   // multiple of 4 nodes at or below the first node of lane 0
   const int xs = (2 * pfirst) & ~3, xoff = 2 * pfirst - xs;
 
-  // ---- producer: thread 0 issues one tensor copy per field per plane (box BX x BY x 1 x 1)
+  // ---- producer: one elected lane of warp 0 issues one tensor copy per field per plane
   int issued = 0, ist = 0;
-  auto issue_plane = [&]() {
-    if (tid == 0) {
+  auto issue_plane = [&]() {         // warp 0 only (warp-uniform)
+    if (elect_one()) {
       uint64_t* bar = full + ist;
       float* dst = ring + ist * stage_floats;
       mbar_arrive_expect_tx(bar, (uint32_t)(NF * BX * p.BY * 4));
@@ -283,12 +308,13 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     for (int s = 0; s < S; ++s) mbar_init(full + s, 1);
     fence_mbar_init();
   }
+  for (int i = tid; i < 2 * XB; i += NT) xbuf[i] = 0.f;
   pdl_wait();
-  {
+  __syncthreads();
+  if (warp == 0) {
     const int n0 = min(S, npl);
     for (int q = 0; q < n0; ++q) issue_plane();
   }
-  __syncthreads();
 
   // ---- thread geometry
   const int r_raw = tid / LXT, lx = tid - r_raw * LXT;
@@ -298,16 +324,23 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   const int r = (r_raw < TR) ? r_raw : 0;        // idle threads shadow a valid position (results dropped)
   const int x0 = 2 * pp;
   const bool has_right = (x0 + 2) < nx;
+  const bool edge_warp = __any_sync(0xffffffffu, !has_right);   // the phantom last element of a row is in this warp
   const int er = jf + r;                         // element row == its upper node row (a); b = er + 1
   const bool own_x = lx >= p.hl;
   const bool own_a = rvalid && own_x && (er >= ty0);   // node row a is stored by this thread; element row owned
   const bool own_b = rvalid && own_x && (r == TR - 1) && (ty1 == p.ny);   // the domain's last node row
-  const bool left_ok = (lx > 0) && (pp > 0);     // a valid pair sits in the lane to the left
+  const bool any_b = __any_sync(0xffffffffu, own_b);
   const float2 vw = f2(1.f, has_right ? 1.f : 0.f);
   const K3& k = p.k3;
-  const float* sbase = ring + r * BX + xoff + 2 * (lvalid ? lx : p.hl);
-  float* gout = p.grad ? p.grad + (((long long)b * p.nz) * p.ny + er) * nx + (lvalid ? x0 : 0) : nullptr;
+  const int rowoff = r * BX + xoff + 2 * (lvalid ? lx : p.hl);   // (row a, node x0) inside a field tile
+  float* gptr = p.grad ? p.grad + ((((long long)b * p.nz + zf) * p.ny + er) * nx + (lvalid ? x0 : 0)) : nullptr;
   const long long plane_elems = (long long)p.ny * nx;
+  const bool st_a = own_a && (gptr != nullptr), st_b = own_b && (gptr != nullptr);
+  const float ew = own_a ? 1.f : 0.f;            // energy weight of this thread's element row
+  const int elo = max(z0, p.zloss_lo), ehi = p.zloss_hi;
+  const bool resid = (p.mode != 0);
+  // where this thread's right-neighbour shares go (trash for the last lane of a row / no pair)
+  const int hw = ((lx == LXT - 1) || !lvalid) ? (XL - 1) : (tid + LXT + 1);
 
   // node planes alternate between two register sets: the upper faces of one layer are the
   // lower faces of the next (no copies)
@@ -316,94 +349,92 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   RowG up;                                       // z-carry of the gradient (row space), upper plane
   up.sa = up.da = up.sb = up.db = f2(0.f);
   double acc = 0.0;
+  float e32 = 0.f;
   int st = 0;
   uint32_t phase = 0;
-  int par = 0;
 
+  auto load_plane = [&](Plane& U) {
+    mbar_wait(full + st, phase);
+    F::load_faces(p, ring + st * stage_floats + rowoff, BX, fstride, has_right, edge_warp, any_b, U.u, U.n, U.f,
+                  U.keep_a, U.keep_b);
+  };
+  auto advance = [&]() {                         // after the CTA barrier: the stage is free again
+    if (warp == 0 && issued < npl) issue_plane();
+    ++st;
+    if (st == S) { st = 0; phase ^= 1u; }
+  };
   // publish the row-b partial sums and the right-neighbour shares of a finished plane
-  auto publish = [&](const RowG& d, float2& Na01, float2& Nb01) {
+  auto publish = [&](const RowG& d, float* xb, float2& Na01, float2& Nb01) {
     const float2 loa = sub2(d.sa, d.da), hia = add2(d.sa, d.da);
     const float2 lob = sub2(d.sb, d.db), hib = add2(d.sb, d.db);
     Na01 = f2(loa.x, loa.y + hia.x);
     Nb01 = f2(lob.x, lob.y + hib.x);
-    float* xb = xbuf + par * 4 * NT;
-    *reinterpret_cast<float2*>(xb + 2 * tid) = Nb01;
-    xb[2 * NT + tid] = hib.y;
-    xb[3 * NT + tid] = hia.y;
+    *reinterpret_cast<float2*>(xb + 2 * (tid + LXT)) = Nb01;
+    xb[HB + hw] = hib.y;
+    xb[HA + hw] = hia.y;
   };
   // after the barrier: gather the neighbours' shares for node row a (and b for the last row)
-  auto finalize = [&](float2 Na01, float2 Nb01, float2 keep_a, float2 keep_b, int zp, int bufpar) {
-    const float* xb = xbuf + bufpar * 4 * NT;
-    const bool zown = (zp >= z0) && (zp < z1);
-    if (own_a) {
-      float2 G = Na01;
-      if (r > 0) G = add2(G, *reinterpret_cast<const float2*>(xb + 2 * (tid - LXT)));
-      if (left_ok) {
-        G.x += xb[3 * NT + tid - 1];
-        if (r > 0) G.x += xb[2 * NT + tid - LXT - 1];
-      }
-      G = mul2(G, keep_a);
-      if (zown) {
-        if (gout) *reinterpret_cast<float2*>(gout + (long long)zp * plane_elems) = G;
-        if (p.mode != 0) acc += (double)(G.x * G.x + G.y * G.y);
-      }
-    }
-    if (own_b) {
-      float2 G = Nb01;
-      if (left_ok) G.x += xb[2 * NT + tid - 1];
-      G = mul2(G, keep_b);
-      if (zown) {
-        if (gout) *reinterpret_cast<float2*>(gout + (long long)zp * plane_elems + nx) = G;
-        if (p.mode != 0) acc += (double)(G.x * G.x + G.y * G.y);
+  auto finalize = [&](float2 Na01, float2 Nb01, float2 keep_a, float2 keep_b, const float* xb, const bool sto) {
+    const float2 nb = *reinterpret_cast<const float2*>(xb + 2 * tid);        // row r-1, same lane
+    // row a from lane lx-1 (thread tid-1), row b of row r-1 from lane lx-1 (thread tid-LXT-1)
+    float2 G = f2(Na01.x + nb.x + (xb[HA + tid + LXT] + xb[HB + tid]), Na01.y + nb.y);
+    G = mul2(G, keep_a);
+    if (sto) {
+      if (st_a) *reinterpret_cast<float2*>(gptr) = G;
+      if (resid && own_a) e32 += G.x * G.x + G.y * G.y;
+      if (any_b) {
+        if (own_b) {
+          float2 Gb = f2(Nb01.x + xb[HB + tid + LXT], Nb01.y);               // row b from lane lx-1
+          Gb = mul2(Gb, keep_b);
+          if (st_b) *reinterpret_cast<float2*>(gptr + nx) = Gb;
+          if (resid) e32 += Gb.x * Gb.x + Gb.y * Gb.y;
+        }
       }
     }
-  };
-  auto next_stage = [&]() {
-    if (issued < npl) issue_plane();
-    ++st;
-    if (st == S) { st = 0; phase ^= 1u; }
+    gptr += plane_elems;
   };
 
   // ---- first plane: nothing below it
-  mbar_wait(full + st, phase);
-  F::load_faces(p, sbase + st * stage_floats, BX, fstride, has_right, PA.u, PA.n, PA.f, PA.keep_a, PA.keep_b);
+  load_plane(PA);
   __syncthreads();
-  next_stage();
+  advance();
 
   // element layer s between plane s (L, registers) and plane s+1 (U, arriving)
-  auto layer = [&](Plane& L, Plane& U, int s) {
-    mbar_wait(full + st, phase);
-    F::load_faces(p, sbase + st * stage_floats, BX, fstride, has_right, U.u, U.n, U.f, U.keep_a, U.keep_b);
+  auto layer = [&](Plane& L, Plane& U, const int s, float* xb) {
+    load_plane(U);
     Face gLo, gUp;
     const float2 E = F::elem_pair(k, L.u, U.u, L.n, U.n, L.f, U.f, vw, gLo, gUp);
-    if (p.mode == 0 && own_a && s >= z0 && s >= p.zloss_lo && s < p.zloss_hi) acc += (double)(E.x + E.y);
+    if (!resid && s >= elo && s < ehi) e32 = fmaf(ew, E.x + E.y, e32);
     const RowG lo = face_to_rows(gLo);
     RowG done;
     done.sa = add2(up.sa, lo.sa); done.da = add2(up.da, lo.da);
     done.sb = add2(up.sb, lo.sb); done.db = add2(up.db, lo.db);
     up = face_to_rows(gUp);
     float2 Na01, Nb01;
-    publish(done, Na01, Nb01);
+    publish(done, xb, Na01, Nb01);
     __syncthreads();       // stage consumed by every thread; partial sums of plane s visible
-    next_stage();
-    finalize(Na01, Nb01, L.keep_a, L.keep_b, s, par);
-    par ^= 1;
+    advance();
+    finalize(Na01, Nb01, L.keep_a, L.keep_b, xb, s >= z0);
   };
   int s = zf;
   for (; s + 1 < zl; s += 2) {
-    layer(PA, PB, s);
-    layer(PB, PA, s + 1);
+    layer(PA, PB, s, xbuf);
+    layer(PB, PA, s + 1, xbuf + XB);
+    acc += (double)e32;
+    e32 = 0.f;
   }
   const bool odd = s < zl;
-  if (odd) layer(PA, PB, s);
+  if (odd) layer(PA, PB, s, xbuf);
 
   // ---- top node plane of the domain: no element layer above it
   if (z1 == p.nz) {
     float2 Na01, Nb01;
-    publish(up, Na01, Nb01);
+    float* xb = odd ? xbuf + XB : xbuf;
+    publish(up, xb, Na01, Nb01);
     __syncthreads();
-    finalize(Na01, Nb01, odd ? PB.keep_a : PA.keep_a, odd ? PB.keep_b : PA.keep_b, p.nz - 1, par);
+    finalize(Na01, Nb01, odd ? PB.keep_a : PA.keep_a, odd ? PB.keep_b : PA.keep_b, xb, true);
   }
+  acc += (double)e32;
 
   pdl_trigger();
   acc = warp_sum(acc);
@@ -411,7 +442,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   __syncthreads();
   double cta = 0.0;
   if (tid == 0)
-    for (int w = 0; w < nw; ++w) cta += s_red[w];
+    for (int w = 0; w < (NT >> 5); ++w) cta += s_red[w];
   finish_loss_w0(p.red, cta);
 }
 

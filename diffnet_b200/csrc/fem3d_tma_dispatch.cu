@@ -83,8 +83,8 @@ struct Plan3T {
   size_t smem;
 };
 
-static size_t smem_3t(int S, int nf, int fstride, int threads) {
-  return (size_t)S * nf * fstride * 4 + (size_t)S * 8 + (size_t)2 * 4 * threads * 4 + 64;
+static size_t smem_3t(int S, int nf, int fstride, int threads, int LXT) {
+  return (size_t)S * nf * fstride * 4 + (size_t)S * 8 + (size_t)2 * xbuf_floats(threads, LXT) * 4 + 64;
 }
 
 // Launch shape search.  Candidates: x-tile width (owned element pairs per tile row) x thread rows
@@ -135,8 +135,8 @@ static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_v
       if (threads > maxt_variant) continue;
       const int fstride = (BX * BY + 31) / 32 * 32;
       int S = S0;
-      while (S > 2 && smem_3t(S, nf, fstride, threads) > (size_t)kMaxDynSmem) --S;
-      const size_t smem = smem_3t(S, nf, fstride, threads);
+      while (S > 2 && smem_3t(S, nf, fstride, threads, LXT) > (size_t)kMaxDynSmem) --S;
+      const size_t smem = smem_3t(S, nf, fstride, threads, LXT);
       if (smem > (size_t)kMaxDynSmem) continue;
       int cps = occ ? occ(threads, smem) : (int)(65536 / (threads * (maxt_variant > 512 ? 96 : 128)));
       if (env_i3("DN_DEBUG_PLAN", 0) >= 2)
