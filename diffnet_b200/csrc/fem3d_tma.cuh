@@ -42,6 +42,11 @@ namespace dn {
 // pair-replicated constants (half-gradient convention: k, not 2k)
 struct K3 {
   float2 kx, ky, kz, kxt, kyt, kzt, kxtt, kytt, kztt, t, tt, nkf, nkft, nkftt, nkfttt, c0x, c0y, c0z;
+  // Isotropic spacing (hx == hy == hz, every BASELINE grid): the stiffness part of E and g is linear
+  // in k, so k is applied once per NODE (kscale, folded into the Dirichlet keep factor) and once per
+  // thread (the energy weight) instead of 12 times per element; the source constants are divided
+  // by k to compensate.  iso == 0: kscale == 1 and the per-direction constants above are used.
+  float kscale;
 };
 
 struct P3T {
@@ -70,6 +75,36 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, in
       : "memory");
 }
 
+// Shared-memory accesses by 32-bit shared-window address (one register per address, [R + imm] forms).
+// volatile: they keep their program order relative to the mbarrier waits and the CTA barrier.
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y));
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "DN_WAIT3:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DN_DONE3;\n"
+      "bra DN_WAIT3;\n"
+      "DN_DONE3:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
 // Face modes of one field for a pair of elements; index bit0 = x, bit1 = y; set bit = difference.
 struct Face {
   float2 m0, m1, m2, m3;
@@ -87,7 +122,7 @@ __device__ __forceinline__ void dir_q(float2 d0, float2 d1, float2 d2, float2 d3
   q3 = fma2(d0, Q33, fma2(d1, Q2, fma2(d2, Q1, mul2(d3, P0))));
 }
 
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI = true>
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI = true, bool ISO = false>
 struct Fem3T {
   static constexpr int NF = 1 + (HAS_NU ? 1 : 0) + (HAS_F ? 1 : 0) + (NUMASK ? 1 : 0) + NM + (VF ? 1 : 0);
   static constexpr int F_U = 0, F_NU = 1, F_F = F_NU + (HAS_NU ? 1 : 0), F_NM = F_F + (HAS_F ? 1 : 0),
@@ -101,23 +136,23 @@ struct Fem3T {
 
   // Read node rows a (local row r) and b (r+1) of one plane from its ring stage, apply the
   // Dirichlet conditions / nu mask, and reduce to the face modes of u, nu, f.
-  // `sp` points at (row r, column x0) of field 0; `fstride` floats between fields.
-  // `edge_warp` / `any_b` are warp-uniform: the phantom last element of a row / the domain's last
-  // node row live in this warp (the common warps skip that work with one branch).
-  static __device__ __forceinline__ void load_faces(const P3T& p, const float* __restrict__ sp, int BX,
-                                                    int fstride, bool has_right, bool edge_warp, bool any_b,
-                                                    Face& Uu, Face& Un, Face& Uf, float2& keep_a,
-                                                    float2& keep_b) {
+  // `a0` = shared-window address of (row r, node x0) of field 0; `fs4` / `bx4` = bytes between
+  // fields / rows.  keep = kscale at free nodes of row a, 0 at Dirichlet nodes.
+  // `edge_warp` is warp-uniform: a phantom element (beyond the last node of a row, or the row below
+  // the domain) lives in this warp; the common warps skip that work with one branch.
+  static __device__ __forceinline__ void load_faces(const P3T& p, uint32_t a0, uint32_t bx4, uint32_t fs4,
+                                                    bool has_right, bool phantom, bool edge_warp, Face& Uu,
+                                                    Face& Un, Face& Uf, float2& keep) {
     float2 su[2], du[2], sn[2], dn_[2], sf[2], df[2];
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
       float v[NF][3];
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
-        const float* q = sp + f * fstride + row * BX;
-        const float2 t = *reinterpret_cast<const float2*>(q);
+        const uint32_t q = a0 + f * fs4 + row * bx4;
+        const float2 t = lds64(q);
         v[f][0] = t.x; v[f][1] = t.y;
-        v[f][2] = q[2];                // beyond the last node the TMA unit has written zeros
+        v[f][2] = lds32(q + 8u);            // beyond the last node the TMA unit has written zeros
       }
       float ub[3], nb[3], fb[3];
       bool fx[3];
@@ -139,20 +174,25 @@ struct Fem3T {
         }
         if constexpr (HAS_F) fb[e] = v[F_F][e];
       }
-      if (row == 0) keep_a = f2(fx[0] ? 0.f : 1.f, fx[1] ? 0.f : 1.f);
-      else if (any_b) keep_b = f2(fx[0] ? 0.f : 1.f, fx[1] ? 0.f : 1.f);
+      if (row == 0) keep = f2(fx[0] ? 0.f : p.k3.kscale, fx[1] ? 0.f : p.k3.kscale);
       xs(ub, su[row], du[row]);
       if constexpr (HAS_NU) xs(nb, sn[row], dn_[row]);
       if constexpr (HAS_F) xs(fb, sf[row], df[row]);
     }
-    // the last element of a row does not exist: E and g are linear in (nu, f), so zeroing
-    // their x-sums/differences removes it (nu == 1 uses the weight vw instead)
-    if (edge_warp) {
-      if (!has_right) {
+    // a phantom element must not contribute: E and g are linear in (nu, f), so zeroing their
+    // x-sums/differences removes it (nu == 1 uses the weight vw instead)
+    if constexpr (HAS_NU || HAS_F) {
+      if (edge_warp) {
 #pragma unroll
         for (int row = 0; row < 2; ++row) {
-          if constexpr (HAS_NU) { sn[row].y = 0.f; dn_[row].y = 0.f; }
-          if constexpr (HAS_F) { sf[row].y = 0.f; df[row].y = 0.f; }
+          if constexpr (HAS_NU) {
+            if (!has_right || phantom) { sn[row].y = 0.f; dn_[row].y = 0.f; }
+            if (phantom) { sn[row].x = 0.f; dn_[row].x = 0.f; }
+          }
+          if constexpr (HAS_F) {
+            if (!has_right || phantom) { sf[row].y = 0.f; df[row].y = 0.f; }
+            if (phantom) { sf[row].x = 0.f; df[row].x = 0.f; }
+          }
         }
       }
     }
@@ -184,15 +224,23 @@ struct Fem3T {
       const float2 C0 = add2(Ln.m0, Un.m0), C1 = add2(Ln.m1, Un.m1), C2 = add2(Ln.m2, Un.m2),
                    C3 = add2(Ln.m3, Un.m3);
       const float2 C4 = sub2(Un.m0, Ln.m0), C5 = sub2(Un.m1, Ln.m1), C6 = sub2(Un.m2, Ln.m2);
+      float2 dx0, dx1, dx2, dx3, dy0, dy1, dy2, dy3, dz0, dz1, dz2, dz3;
+      if constexpr (ISO) {   // k is applied per node / per thread (K3::kscale): 6 products instead of 12
+        const float2 T1 = mul2(k.t, C1), T2 = mul2(k.t, C2), T4 = mul2(k.t, C4);
+        dx0 = C0; dx1 = T2; dx2 = T4; dx3 = mul2(k.tt, C6);
+        dy0 = C0; dy1 = T1; dy2 = T4; dy3 = mul2(k.tt, C5);
+        dz0 = C0; dz1 = T1; dz2 = T2; dz3 = mul2(k.tt, C3);
+      } else {
+        dx0 = mul2(k.kx, C0); dx1 = mul2(k.kxt, C2); dx2 = mul2(k.kxt, C4); dx3 = mul2(k.kxtt, C6);
+        dy0 = mul2(k.ky, C0); dy1 = mul2(k.kyt, C1); dy2 = mul2(k.kyt, C4); dy3 = mul2(k.kytt, C5);
+        dz0 = mul2(k.kz, C0); dz1 = mul2(k.kzt, C1); dz2 = mul2(k.kzt, C2); dz3 = mul2(k.kztt, C3);
+      }
       // d/dx: P = (xi, xi eta, xi zeta, xi eta zeta); nu modes (1, eta, zeta, eta zeta)
-      dir_q(mul2(k.kx, C0), mul2(k.kxt, C2), mul2(k.kxt, C4), mul2(k.kxtt, C6), u1, u3, u5, u7, Q3, Q5,
-            Q7, Q77, qx0, qx1, qx2, qx3);
+      dir_q(dx0, dx1, dx2, dx3, u1, u3, u5, u7, Q3, Q5, Q7, Q77, qx0, qx1, qx2, qx3);
       // d/dy: P = (eta, xi eta, eta zeta, xi eta zeta); nu modes (1, xi, zeta, xi zeta)
-      dir_q(mul2(k.ky, C0), mul2(k.kyt, C1), mul2(k.kyt, C4), mul2(k.kytt, C5), u2, u3, u6, u7, Q3, Q6,
-            Q7, Q77, qy0, qy1, qy2, qy3);
+      dir_q(dy0, dy1, dy2, dy3, u2, u3, u6, u7, Q3, Q6, Q7, Q77, qy0, qy1, qy2, qy3);
       // d/dz: P = (zeta, xi zeta, eta zeta, xi eta zeta); nu modes (1, xi, eta, xi eta)
-      dir_q(mul2(k.kz, C0), mul2(k.kzt, C1), mul2(k.kzt, C2), mul2(k.kztt, C3), u4, u5, u6, u7, Q5, Q6,
-            Q7, Q77, qz0, qz1, qz2, qz3);
+      dir_q(dz0, dz1, dz2, dz3, u4, u5, u6, u7, Q5, Q6, Q7, Q77, qz0, qz1, qz2, qz3);
     } else {
       // nu == 1: C0 = 8 (times the validity weight of the element), all other modes 0
       const float2 dx = mul2(k.c0x, vw), dy = mul2(k.c0y, vw), dz = mul2(k.c0z, vw);
@@ -247,18 +295,23 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// Exchange area of one parity (floats): [nb: 2 (NT + LXT)] [hb: XL] [ha: XL], XL = NT + LXT + 4.
-//   nb  row-b partial sums (float2 per thread), shifted by one tile row so that row 0 reads a
-//       permanently zero prefix;
-//   hb / ha  right-neighbour shares of row b / row a, shifted by one tile row + one lane.  The last
+// Exchange area (gradient gather between thread rows / lanes), FIXED geometry so that every
+// address in the main loop is [thread register + immediate].  Per parity, in floats:
+//   nb  float2[XPRE + MAXT]  row-b partial sums of thread i at slot XPRE + i; the reader (one tile row
+//                            below) reads slot XPRE + i - LXT: row 0 lands in the never-written, zero prefix
+//   hb  float [XPRE + MAXT + 4], ha likewise: right-neighbour shares of row b / row a.  The last
 //       lane of every tile row (its right neighbour belongs to another tile or does not exist) and
-//       lanes that hold no pair store to the trash word at the end of each array, so the slot a
-//       first lane reads stays zero: no predicates in the gather.
-__host__ __device__ __forceinline__ int xbuf_floats(int NT, int LXT) { return 4 * NT + 4 * LXT + 8; }
+//       lanes that hold no pair store to the trash word at the end of each array, so the slot the
+//       first lane of a row reads stays zero: no predicates in the gather.
+constexpr int kXPre = 132;                                   // >= LXT + 1 (BX <= 256 -> LXT <= 126)
+constexpr int kXNb = 0, kXHb = 2 * (kXPre + DN_T3_MAXT), kXHa = kXHb + kXPre + DN_T3_MAXT + 4;
+constexpr int kXParity = kXHa + kXPre + DN_T3_MAXT + 4;      // floats per parity
+constexpr int kXTrash = kXPre + DN_T3_MAXT + 2;              // slot index (within hb / ha) nobody reads
+__host__ __device__ constexpr int xbuf_bytes() { return 2 * kXParity * 4; }
 
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI>
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI, bool ISO>
 __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_constant__ P3T p) {
-  using F = Fem3T<NM, VF, HAS_NU, HAS_F, NUMASK, MI>;
+  using F = Fem3T<NM, VF, HAS_NU, HAS_F, NUMASK, MI, ISO>;
   constexpr int NF = F::NF;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[DN_T3_MAXT / 32];
@@ -270,8 +323,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   const int stage_floats = NF * fstride;
   float* const ring = reinterpret_cast<float*>(smem_raw);                                   // [S][NF][fstride]
   uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats);      // [S]
-  float* const xbuf = reinterpret_cast<float*>(full + S);                                   // [2][xbuf_floats]
-  const int XL = NT + LXT + 4, HB = 2 * (NT + LXT), HA = HB + XL, XB = HA + XL;
+  float* const xbuf = reinterpret_cast<float*>(full + S);                                   // [2][kXParity]
 
   // ---- work item: (b, z-chunk, y-tile, x-tile)
   int w_ = blockIdx.x;
@@ -281,7 +333,10 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   const int b = w_ / p.nzc;
   const int ty0 = ity * p.TY, ty1 = min(p.ny, ty0 + p.TY);      // owned node rows [ty0, ty1)
   const int jf = max(ty0 - 1, 0), jl = min(ty1, p.ny - 1);       // node rows needed: jf..jl
-  const int TR = jl - jf;                                        // element rows of this tile
+  // element rows of this tile; the tile that holds the domain's last node row runs one PHANTOM
+  // element row below it (nodes beyond the domain are zero-filled by the TMA unit, its nu / f / weight
+  // are zeroed), so that the last node row is gathered and stored like every other row
+  const int TRr = jl - jf, TR = TRr + (ty1 == p.ny ? 1 : 0);
   const int z0 = izc * p.ZC, z1 = min(p.nz, z0 + p.ZC);          // owned node planes [z0, z1)
   const int zf = max(z0 - 1, 0), zl = min(z1, p.nz - 1);         // planes loaded: zf..zl
   const int npl = zl - zf + 1;                                   // >= 2
@@ -308,7 +363,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     for (int s = 0; s < S; ++s) mbar_init(full + s, 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < 2 * XB; i += NT) xbuf[i] = 0.f;
+  for (int i = tid; i < 2 * kXParity; i += NT) xbuf[i] = 0.f;
   pdl_wait();
   __syncthreads();
   if (warp == 0) {
@@ -324,27 +379,36 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   const int r = (r_raw < TR) ? r_raw : 0;        // idle threads shadow a valid position (results dropped)
   const int x0 = 2 * pp;
   const bool has_right = (x0 + 2) < nx;
-  const bool edge_warp = __any_sync(0xffffffffu, !has_right);   // the phantom last element of a row is in this warp
+  const bool phantom = (r >= TRr);               // the element row below the domain's last node row
+  // the phantom last element of a row / the phantom row is in this warp (the common warps skip that work)
+  const bool edge_warp = __any_sync(0xffffffffu, !has_right || phantom);
   const int er = jf + r;                         // element row == its upper node row (a); b = er + 1
-  const bool own_x = lx >= p.hl;
-  const bool own_a = rvalid && own_x && (er >= ty0);   // node row a is stored by this thread; element row owned
-  const bool own_b = rvalid && own_x && (r == TR - 1) && (ty1 == p.ny);   // the domain's last node row
-  const bool any_b = __any_sync(0xffffffffu, own_b);
-  const float2 vw = f2(1.f, has_right ? 1.f : 0.f);
+  const bool own_a = rvalid && (lx >= p.hl) && (er >= ty0);   // node row a is stored by this thread; element row owned
+  const float2 vw = f2(phantom ? 0.f : 1.f, (has_right && !phantom) ? 1.f : 0.f);
   const K3& k = p.k3;
-  const int rowoff = r * BX + xoff + 2 * (lvalid ? lx : p.hl);   // (row a, node x0) inside a field tile
   float* gptr = p.grad ? p.grad + ((((long long)b * p.nz + zf) * p.ny + er) * nx + (lvalid ? x0 : 0)) : nullptr;
   const long long plane_elems = (long long)p.ny * nx;
-  const bool st_a = own_a && (gptr != nullptr), st_b = own_b && (gptr != nullptr);
-  const float ew = own_a ? 1.f : 0.f;            // energy weight of this thread's element row
-  const int elo = max(z0, p.zloss_lo), ehi = p.zloss_hi;
+  const bool st_a = own_a && (gptr != nullptr);
+  const float ew = (own_a && !phantom) ? k.kscale : 0.f;   // energy weight of this thread's element row
+  const int elo = max(z0, p.zloss_lo), ecnt = p.zloss_hi - elo;
   const bool resid = (p.mode != 0);
-  // where this thread's right-neighbour shares go (trash for the last lane of a row / no pair)
-  const int hw = ((lx == LXT - 1) || !lvalid) ? (XL - 1) : (tid + LXT + 1);
+
+  // ---- shared-window addresses (bytes): the ring row of this thread, its exchange slots
+  const uint32_t fs4 = 4u * fstride, bx4 = 4u * BX, stage4 = 4u * stage_floats;
+  const uint32_t row0 = smem_u32(ring) + 4u * (r * BX + xoff + 2 * (lvalid ? lx : p.hl));   // (row a, node x0), stage 0
+  uint32_t cur = row0;
+  uint32_t cbar = smem_u32(full);
+  const uint32_t xb0 = smem_u32(xbuf);
+  const uint32_t a_nw = xb0 + 8u * (kXPre + tid);                 // nb[tid]      (write)
+  const uint32_t a_nr = a_nw - 8u * LXT;                          // nb[tid-LXT]  (read: row r-1, same lane)
+  const uint32_t a_t4 = xb0 + 4u * (kXHb + kXPre + tid);          // hb[tid]; ha[tid] is 4 (kXHa - kXHb) further
+  const uint32_t a_r4 = a_t4 - 4u * LXT;                          // hb[tid-LXT]
+  const uint32_t a_hw = ((lx == LXT - 1) || !lvalid) ? xb0 + 4u * (kXHb + kXTrash) : a_t4;   // where the shares go
+  constexpr uint32_t kHA = 4u * (kXHa - kXHb), kPAR = 4u * kXParity;
 
   // node planes alternate between two register sets: the upper faces of one layer are the
   // lower faces of the next (no copies)
-  struct Plane { Face u, n, f; float2 keep_a, keep_b; };
+  struct Plane { Face u, n, f; float2 keep; };
   Plane PA, PB;
   RowG up;                                       // z-carry of the gradient (row space), upper plane
   up.sa = up.da = up.sb = up.db = f2(0.f);
@@ -354,42 +418,34 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   uint32_t phase = 0;
 
   auto load_plane = [&](Plane& U) {
-    mbar_wait(full + st, phase);
-    F::load_faces(p, ring + st * stage_floats + rowoff, BX, fstride, has_right, edge_warp, any_b, U.u, U.n, U.f,
-                  U.keep_a, U.keep_b);
+    mbar_wait_u32(cbar, phase);
+    F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, U.u, U.n, U.f, U.keep);
   };
   auto advance = [&]() {                         // after the CTA barrier: the stage is free again
     if (warp == 0 && issued < npl) issue_plane();
-    ++st;
-    if (st == S) { st = 0; phase ^= 1u; }
+    ++st; cur += stage4; cbar += 8u;
+    if (st == S) { st = 0; cur = row0; cbar -= 8u * S; phase ^= 1u; }
   };
-  // publish the row-b partial sums and the right-neighbour shares of a finished plane
-  auto publish = [&](const RowG& d, float* xb, float2& Na01, float2& Nb01) {
+  // publish the row-b partial sums and the right-neighbour shares of a finished plane; returns the
+  // part of node row a this thread already holds
+  auto publish = [&](const RowG& d, const uint32_t po) -> float2 {
     const float2 loa = sub2(d.sa, d.da), hia = add2(d.sa, d.da);
     const float2 lob = sub2(d.sb, d.db), hib = add2(d.sb, d.db);
-    Na01 = f2(loa.x, loa.y + hia.x);
-    Nb01 = f2(lob.x, lob.y + hib.x);
-    *reinterpret_cast<float2*>(xb + 2 * (tid + LXT)) = Nb01;
-    xb[HB + hw] = hib.y;
-    xb[HA + hw] = hia.y;
+    sts64(a_nw + po, f2(lob.x, lob.y + hib.x));
+    sts32(a_hw + po, hib.y);
+    sts32(a_hw + kHA + po, hia.y);
+    return f2(loa.x, loa.y + hia.x);
   };
-  // after the barrier: gather the neighbours' shares for node row a (and b for the last row)
-  auto finalize = [&](float2 Na01, float2 Nb01, float2 keep_a, float2 keep_b, const float* xb, const bool sto) {
-    const float2 nb = *reinterpret_cast<const float2*>(xb + 2 * tid);        // row r-1, same lane
-    // row a from lane lx-1 (thread tid-1), row b of row r-1 from lane lx-1 (thread tid-LXT-1)
-    float2 G = f2(Na01.x + nb.x + (xb[HA + tid + LXT] + xb[HB + tid]), Na01.y + nb.y);
-    G = mul2(G, keep_a);
+  // after the barrier: gather the neighbours' shares for node row a, mask, store
+  auto finalize = [&](float2 Na01, float2 keep, const uint32_t po, const bool sto) {
+    const float2 nb = lds64(a_nr + po);                            // row r-1, same lane
+    const float ha = lds32(a_t4 + kHA - 4u + po);                  // row a from lane lx-1   (thread tid-1)
+    const float hb = lds32(a_r4 - 4u + po);                        // row b of row r-1 from lane lx-1 (thread tid-LXT-1)
+    float2 G = f2(Na01.x + nb.x + (ha + hb), Na01.y + nb.y);
+    G = mul2(G, keep);
     if (sto) {
       if (st_a) *reinterpret_cast<float2*>(gptr) = G;
       if (resid && own_a) e32 += G.x * G.x + G.y * G.y;
-      if (any_b) {
-        if (own_b) {
-          float2 Gb = f2(Nb01.x + xb[HB + tid + LXT], Nb01.y);               // row b from lane lx-1
-          Gb = mul2(Gb, keep_b);
-          if (st_b) *reinterpret_cast<float2*>(gptr + nx) = Gb;
-          if (resid) e32 += Gb.x * Gb.x + Gb.y * Gb.y;
-        }
-      }
     }
     gptr += plane_elems;
   };
@@ -400,39 +456,38 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   advance();
 
   // element layer s between plane s (L, registers) and plane s+1 (U, arriving)
-  auto layer = [&](Plane& L, Plane& U, const int s, float* xb) {
+  auto layer = [&](Plane& L, Plane& U, const int s, const uint32_t po) {
     load_plane(U);
     Face gLo, gUp;
     const float2 E = F::elem_pair(k, L.u, U.u, L.n, U.n, L.f, U.f, vw, gLo, gUp);
-    if (!resid && s >= elo && s < ehi) e32 = fmaf(ew, E.x + E.y, e32);
+    const float wl = (!resid && (unsigned)(s - elo) < (unsigned)ecnt) ? ew : 0.f;
+    e32 = fmaf(wl, E.x + E.y, e32);
     const RowG lo = face_to_rows(gLo);
     RowG done;
     done.sa = add2(up.sa, lo.sa); done.da = add2(up.da, lo.da);
     done.sb = add2(up.sb, lo.sb); done.db = add2(up.db, lo.db);
     up = face_to_rows(gUp);
-    float2 Na01, Nb01;
-    publish(done, xb, Na01, Nb01);
+    const float2 Na01 = publish(done, po);
     __syncthreads();       // stage consumed by every thread; partial sums of plane s visible
     advance();
-    finalize(Na01, Nb01, L.keep_a, L.keep_b, xb, s >= z0);
+    finalize(Na01, L.keep, po, s >= z0);
   };
   int s = zf;
   for (; s + 1 < zl; s += 2) {
-    layer(PA, PB, s, xbuf);
-    layer(PB, PA, s + 1, xbuf + XB);
+    layer(PA, PB, s, 0u);
+    layer(PB, PA, s + 1, kPAR);
     acc += (double)e32;
     e32 = 0.f;
   }
   const bool odd = s < zl;
-  if (odd) layer(PA, PB, s, xbuf);
+  if (odd) layer(PA, PB, s, 0u);
 
   // ---- top node plane of the domain: no element layer above it
   if (z1 == p.nz) {
-    float2 Na01, Nb01;
-    float* xb = odd ? xbuf + XB : xbuf;
-    publish(up, xb, Na01, Nb01);
+    const uint32_t po = odd ? kPAR : 0u;
+    const float2 Na01 = publish(up, po);
     __syncthreads();
-    finalize(Na01, Nb01, odd ? PB.keep_a : PA.keep_a, odd ? PB.keep_b : PA.keep_b, xb, true);
+    finalize(Na01, odd ? PB.keep : PA.keep, po, true);
   }
   acc += (double)e32;
 
@@ -452,29 +507,29 @@ typedef int (*occ3t_fn)(int, size_t);
 launch3t_fn get_launch3t(int MK, int NU, int F, int NUMASK);
 occ3t_fn get_occ3t(int MK, int NU, int F, int NUMASK);
 
-template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int MK, int NUK, bool HAS_F, bool NUMASK>
 struct Kern3T {
   // MK 0..3 / 4 / 5..7 as in fem2d_tma.cuh (5..7: mask_input = 0)
   static constexpr int NM = (MK == 4) ? 1 : (MK >= 5 ? MK - 4 : MK);
-  static auto get() { return k_fem3d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK, (MK < 5)>; }
+  static auto get() { return k_fem3d_tma<NM, (MK == 4), (NUK != 0), HAS_F, NUMASK, (MK < 5), (NUK == 2)>; }
 };
 
-template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int MK, int NUK, bool HAS_F, bool NUMASK>
 cudaError_t prep3t() {
   static bool done[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  e = cudaFuncSetAttribute(Kern3T<MK, HAS_NU, HAS_F, NUMASK>::get(),
+  e = cudaFuncSetAttribute(Kern3T<MK, NUK, HAS_F, NUMASK>::get(),
                            cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
   if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
   return e;
 }
 
-template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int MK, int NUK, bool HAS_F, bool NUMASK>
 cudaError_t launch3t(const P3T& p, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
-  cudaError_t e = prep3t<MK, HAS_NU, HAS_F, NUMASK>();
+  cudaError_t e = prep3t<MK, NUK, HAS_F, NUMASK>();
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -483,14 +538,14 @@ cudaError_t launch3t(const P3T& p, dim3 grid, dim3 block, size_t smem, cudaStrea
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   if (pdl_enabled()) { cfg.attrs = at; cfg.numAttrs = 1; }
-  return cudaLaunchKernelEx(&cfg, Kern3T<MK, HAS_NU, HAS_F, NUMASK>::get(), p);
+  return cudaLaunchKernelEx(&cfg, Kern3T<MK, NUK, HAS_F, NUMASK>::get(), p);
 }
 
-template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int MK, int NUK, bool HAS_F, bool NUMASK>
 int occ3t(int threads, size_t smem) {
-  if (prep3t<MK, HAS_NU, HAS_F, NUMASK>() != cudaSuccess) return 0;
+  if (prep3t<MK, NUK, HAS_F, NUMASK>() != cudaSuccess) return 0;
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern3T<MK, HAS_NU, HAS_F, NUMASK>::get(), threads,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern3T<MK, NUK, HAS_F, NUMASK>::get(), threads,
                                                     smem) != cudaSuccess)
     return 0;
   return n;

@@ -83,8 +83,8 @@ struct Plan3T {
   size_t smem;
 };
 
-static size_t smem_3t(int S, int nf, int fstride, int threads, int LXT) {
-  return (size_t)S * nf * fstride * 4 + (size_t)S * 8 + (size_t)2 * xbuf_floats(threads, LXT) * 4 + 64;
+static size_t smem_3t(int S, int nf, int fstride) {
+  return (size_t)S * nf * fstride * 4 + (size_t)S * 8 + (size_t)xbuf_bytes() + 64;
 }
 
 // Launch shape search.  Candidates: x-tile width (owned element pairs per tile row) x thread rows
@@ -124,8 +124,9 @@ static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_v
       if (ty_forced > 0) { if (ty_forced > TYmax) continue; TYmax = ty_forced; }
       const int nty = (g->ny + TYmax - 1) / TYmax;
       const int TY = (g->ny + nty - 1) / nty;
-      // element rows a tile runs: TY+1 with a halo row above (interior tiles), fewer at the domain edges
-      int need = nty >= 3 ? TY + 1 : (nty == 2 ? TY : TY - 1);
+      // thread rows a tile needs: TY owned node rows + the halo element row above (tiles below the
+      // first); the tile with the domain's last node row runs a phantom element row below it instead
+      int need = nty >= 2 ? TY + 1 : TY;
       if (need < 1) need = 1;
       if (ty_forced <= 0 && rows != need && !(need < 2 && rows == 2)) continue;   // a smaller block covers it
       if (rows < need) continue;
@@ -135,8 +136,8 @@ static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_v
       if (threads > maxt_variant) continue;
       const int fstride = (BX * BY + 31) / 32 * 32;
       int S = S0;
-      while (S > 2 && smem_3t(S, nf, fstride, threads, LXT) > (size_t)kMaxDynSmem) --S;
-      const size_t smem = smem_3t(S, nf, fstride, threads, LXT);
+      while (S > 2 && smem_3t(S, nf, fstride) > (size_t)kMaxDynSmem) --S;
+      const size_t smem = smem_3t(S, nf, fstride);
       if (smem > (size_t)kMaxDynSmem) continue;
       int cps = occ ? occ(threads, smem) : (int)(65536 / (threads * (maxt_variant > 512 ? 96 : 128)));
       if (env_i3("DN_DEBUG_PLAN", 0) >= 2)
@@ -203,7 +204,8 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   const char* path = getenv("DN_3D_PATH");
   if (path && !strcmp(path, "tile")) return DN_OK;
   if (!vec4 || fgp.p || ((uintptr_t)grad % 16 != 0)) return DN_OK;
-  const int NU = nu.p ? 1 : 0, F = f.p ? 1 : 0, NMK = numask.p ? 1 : 0;
+  const bool iso = nu.p && k.kx == k.ky && k.kx == k.kz && k.kx != 0.f && env_i3("DN_T3_ISO", 1);
+  const int NU = nu.p ? (iso ? 2 : 1) : 0, F = f.p ? 1 : 0, NMK = numask.p ? 1 : 0;
   int MKx = MK;
   if (!mask_input) {                     // operator apply: only the plain-mask, no-source variants exist
     if (MK == 0) MKx = 0;
@@ -248,6 +250,13 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   p.k3.nkf = pr(-k.kf); p.k3.nkft = pr(-k.kf * t); p.k3.nkftt = pr(-k.kf * t * t);
   p.k3.nkfttt = pr(-k.kf * t * t * t);
   p.k3.c0x = pr(8.f * k.kx); p.k3.c0y = pr(8.f * k.ky); p.k3.c0z = pr(8.f * k.kz);
+  p.k3.kscale = 1.f;
+  if (iso) {
+    // isotropic spacing: k moves out of the element (see K3); the source constants absorb 1/k
+    p.k3.kscale = k.kx;
+    const float kf = k.kf / k.kx;
+    p.k3.nkf = pr(-kf); p.k3.nkft = pr(-kf * t); p.k3.nkftt = pr(-kf * t * t); p.k3.nkfttt = pr(-kf * t * t * t);
+  }
   p.grad = grad;
   p.red.counter = (unsigned int*)workspace;
   p.red.partials = (double*)((char*)workspace + 64);
