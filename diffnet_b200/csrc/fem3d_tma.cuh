@@ -322,8 +322,8 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   const int nx = p.nx, LXT = p.LXT, S = p.S, BX = p.BX, fstride = p.fstride;
   const int stage_floats = NF * fstride;
   float* const ring = reinterpret_cast<float*>(smem_raw);                                   // [S][NF][fstride]
-  uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats);      // [S]
-  float* const xbuf = reinterpret_cast<float*>(full + S);                                   // [2][kXParity]
+  uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats);      // [S] + 1: the layer barrier
+  float* const xbuf = reinterpret_cast<float*>(full + S + 1);                               // [2][kXParity]
 
   // ---- work item: (b, z-chunk, y-tile, x-tile)
   int w_ = blockIdx.x;
@@ -361,6 +361,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   };
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(full + s, 1);
+    mbar_init(full + S, NT >> 5);                  // split-phase CTA barrier: one arrival per warp and layer
     fence_mbar_init();
   }
   for (int i = tid; i < 2 * kXParity; i += NT) xbuf[i] = 0.f;
@@ -417,14 +418,30 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   int st = 0;
   uint32_t phase = 0;
 
-  auto load_plane = [&](Plane& U) {
+  // The per-layer CTA barrier is SPLIT (an mbarrier, one arrival per warp): a warp arrives as soon as
+  // its partial sums of plane s are published, then already fetches plane s+2 and reduces it to face
+  // modes (into the register set of the plane it has just finished with) and only then waits for the
+  // other warps, refills the ring and gathers plane s.  Warps that finish the element math early thus
+  // run their load/mask phase while the others still compute: the two phases overlap across warps
+  // instead of every warp stalling on the same latency at the same time.
+  const uint32_t lbar = smem_u32(full + S);
+  uint32_t lphase = 0;
+  auto arrive = [&]() {
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lbar) : "memory");
+  };
+  auto wait_all = [&]() {
+    mbar_wait_u32(lbar, lphase);
+    lphase ^= 1u;
+  };
+  auto load_next = [&](Plane& U) {               // next ring stage: wait for its plane (long since requested), read it
+    ++st; cur += stage4; cbar += 8u;
+    if (st == S) { st = 0; cur = row0; cbar -= 8u * S; phase ^= 1u; }
     mbar_wait_u32(cbar, phase);
     F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, U.u, U.n, U.f, U.keep);
   };
-  auto advance = [&]() {                         // after the CTA barrier: the stage is free again
+  auto refill = [&]() {                          // after the layer barrier: the oldest stage is free again
     if (warp == 0 && issued < npl) issue_plane();
-    ++st; cur += stage4; cbar += 8u;
-    if (st == S) { st = 0; cur = row0; cbar -= 8u * S; phase ^= 1u; }
   };
   // publish the row-b partial sums and the right-neighbour shares of a finished plane; returns the
   // part of node row a this thread already holds
@@ -450,14 +467,16 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     gptr += plane_elems;
   };
 
-  // ---- first plane: nothing below it
-  load_plane(PA);
-  __syncthreads();
-  advance();
+  // ---- first two planes (npl >= 2): nothing below the first
+  mbar_wait_u32(cbar, phase);
+  F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, PA.u, PA.n, PA.f, PA.keep);
+  arrive();
+  load_next(PB);
+  wait_all();
+  refill();                  // the stage of the first plane
 
-  // element layer s between plane s (L, registers) and plane s+1 (U, arriving)
+  // element layer s between plane s (L) and plane s+1 (U), both in registers
   auto layer = [&](Plane& L, Plane& U, const int s, const uint32_t po) {
-    load_plane(U);
     Face gLo, gUp;
     const float2 E = F::elem_pair(k, L.u, U.u, L.n, U.n, L.f, U.f, vw, gLo, gUp);
     const float wl = (!resid && (unsigned)(s - elo) < (unsigned)ecnt) ? ew : 0.f;
@@ -468,9 +487,12 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     done.sb = add2(up.sb, lo.sb); done.db = add2(up.db, lo.db);
     up = face_to_rows(gUp);
     const float2 Na01 = publish(done, po);
-    __syncthreads();       // stage consumed by every thread; partial sums of plane s visible
-    advance();
-    finalize(Na01, L.keep, po, s >= z0);
+    arrive();              // this warp has read the stage of plane s+1 and published its sums of plane s
+    const float2 keepL = L.keep;
+    if (s + 2 <= zl) load_next(L);      // plane s+2 replaces plane s in registers
+    wait_all();            // every warp has arrived: partial sums of plane s visible, stage of plane s+1 free
+    refill();
+    finalize(Na01, keepL, po, s >= z0);
   };
   int s = zf;
   for (; s + 1 < zl; s += 2) {
@@ -486,7 +508,8 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   if (z1 == p.nz) {
     const uint32_t po = odd ? kPAR : 0u;
     const float2 Na01 = publish(up, po);
-    __syncthreads();
+    arrive();
+    wait_all();
     finalize(Na01, odd ? PB.keep : PA.keep, po, true);
   }
   acc += (double)e32;

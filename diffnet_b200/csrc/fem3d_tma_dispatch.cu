@@ -84,7 +84,7 @@ struct Plan3T {
 };
 
 static size_t smem_3t(int S, int nf, int fstride) {
-  return (size_t)S * nf * fstride * 4 + (size_t)S * 8 + (size_t)xbuf_bytes() + 64;
+  return (size_t)S * nf * fstride * 4 + (size_t)(S + 1) * 8 + (size_t)xbuf_bytes() + 64;
 }
 
 // Launch shape search.  Candidates: x-tile width (owned element pairs per tile row) x thread rows
