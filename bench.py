@@ -145,6 +145,109 @@ def call_kwargs(d):
     return {k: v for k, v in d.items() if not k.startswith("_") and k != "u"}
 
 
+def nsets_for(name):
+    """Input sets a timed run rotates through so that every step streams from HBM, not from the 126 MB L2."""
+    nsd, size, B, bpd, _ = WORKLOADS[name]
+    return min(64, max(2, int(-(-400e6 // (B * size ** nsd * bpd)))))
+
+
+def shared_config(name, world):
+    """The `config` object of the JSON line: identical for --impl ours and --impl reference (the
+    driver compares them); everything arm-specific lives under `run`."""
+    nsd, size, B, bpd, desc = WORKLOADS[name]
+    n = nsets_for(name)
+    return {"workload": name, "desc": desc, "batch_per_gpu": B, "grid": [size] * nsd,
+            "dof_per_step_per_gpu": B * size ** nsd, "fields": "u, nu, f, bc1, bc2 (fp32)" if bpd == 24 else "4 fp32 nodal fields",
+            "bytes_per_dof": bpd,
+            "l2": f"GPU arm: inputs rotated over {n} buffer sets ({n * B * size ** nsd * bpd / 1e6:.0f} MB "
+                  + ("> 126 MB L2" if n * B * size ** nsd * bpd > 126e6 else "-- fits the L2: a launch-latency probe, not a bandwidth number")
+                  + "); CPU arm: host memory",
+            "parallelism": f"dp{world} (batch sharded over the ranks, no data-path collective)"}
+
+
+FLOPS_PER_DOF = {2: 90.0, 3: 280.0}     # closed-form fp32 operations per DOF, fwd + adjoint (SURVEY.md 8d)
+
+
+def time_workload(name, dev, seed, K, W, reps, world=1, barrier=None, use_graph=True):
+    """Device-timed fused loss+gradient launches of one workload on this rank: K launches replayed
+    from one CUDA graph, CUDA events, median of `reps`.  Returns ms per step (this rank) and the mode."""
+    import torch
+    fem = make_fem(name)
+    nsets = nsets_for(name)
+    sets = [make_inputs(name, dev, seed=seed + i) for i in range(nsets)]
+    kws = [call_kwargs(s) for s in sets]
+
+    def launch(i):
+        s = sets[i % nsets]
+        return fem.energy_loss_and_grad(s["u"], **kws[i % nsets])
+
+    for i in range(max(W, 3)):
+        launch(i)
+    torch.cuda.synchronize()
+    mode, graph = "cuda_graph", None
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(2):
+                    launch(i)                      # allocate this stream's workspace before capture
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(K):
+                    launch(i)                      # outputs are recycled by the graph's pool
+            graph.replay()                         # one untimed replay
+            torch.cuda.synchronize()
+        except Exception as e:   # noqa: BLE001
+            graph, mode = None, f"eager (graph capture failed: {type(e).__name__})"
+            torch.cuda.synchronize()
+    else:
+        mode = "eager"
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    for _ in range(reps):
+        if barrier is not None:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        e0.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(K):
+                launch(i)
+        e1.record()
+        if barrier is not None:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms_step = sorted(times)[len(times) // 2] / K
+    return {"ms_step": ms_step, "mode": mode, "sets": sets, "fem": fem, "nsets": nsets}
+
+
+def point_of(name, res, peak, clock_mhz=None):
+    """One entry of `points`: a BASELINE config (or named roofline point) measured like the headline."""
+    nsd, size, B, bpd, desc = WORKLOADS[name]
+    dof = B * size ** nsd
+    ms = res["ms_step"]
+    val = dof / (ms * 1e-3) / 1e9
+    ach = val * bpd
+    fp32_peak = 148 * 128 * 2 * (clock_mhz or 1965.0) * 1e6 / 1e12      # TFLOP/s, FMA = 2
+    return {"value": val, "unit": "GDOF/s", "ms_per_step": ms, "bytes_per_dof": bpd,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak},
+            "secondary": {"bound": "fp32_pipe", "achieved": val * FLOPS_PER_DOF[nsd] / 1e3, "unit": "TFLOP/s",
+                          "peak": fp32_peak, "frac": val * FLOPS_PER_DOF[nsd] / 1e3 / fp32_peak,
+                          "algorithmic_flops_per_dof": FLOPS_PER_DOF[nsd]},
+            "kernel": "k_fem2d_tma" if nsd == 2 else "k_fem3d_tma", "launch": res["mode"], "desc": desc}
+
+
+POINTS = ["poisson2d_512_b16", "ibn2d_512_b16", "poisson3d_param_64_b16", "poisson3d_128_b1", "poisson3d_256_b1",
+          "poisson2d_64_b1"]
+
+
 # ------------------------------------------------------------------------------------ oracle legs
 def oracle_step_time(name, sample_B, threads, repeats=8):
     """fwd+bwd of the oracle (reference conv path restated) on the CPU; best of `repeats`."""
@@ -266,7 +369,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "desc": desc, "cpu_sample": sample},
+        "config": shared_config(name, args.gpus),
+        "run": {"cpu_sample": sample},
         "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -290,76 +394,26 @@ def run_ours(args):
 
     name = args.workload
     nsd, size, B, bpd, desc = WORKLOADS[name]
-    fem = make_fem(name)
     dof_step = B * size ** nsd                     # per GPU per step
     step_bytes = dof_step * bpd
-    # rotate input sets so that every step streams from HBM, not from the 126 MB L2
-    nsets = max(2, int(-(-400e6 // step_bytes)))
-    nsets = min(nsets, 64)
-    sets = [make_inputs(name, dev, seed=1234 + 17 * rank + i) for i in range(nsets)]
-    kws = [call_kwargs(s) for s in sets]
     K, W = args.steps, args.warmup
-
-    def launch(i):
-        s = sets[i % nsets]
-        return fem.energy_loss_and_grad(s["u"], **kws[i % nsets])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (eager), then capture K steps into one CUDA graph
-    for i in range(max(W, 3)):
-        out = launch(i)
-    torch.cuda.synchronize()
-    mode = "cuda_graph"
-    graph = None
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for i in range(2):
-                    launch(i)                      # allocate this stream's workspace before capture
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                for i in range(K):
-                    launch(i)                      # outputs are recycled by the graph's pool
-            graph.replay()                         # one untimed replay
-            torch.cuda.synchronize()
-        except Exception as e:   # noqa: BLE001
-            graph, mode = None, f"eager (graph capture failed: {type(e).__name__})"
-            torch.cuda.synchronize()
-    else:
-        mode = "eager"
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = args.reps
-    times = []
-    for _ in range(reps):
-        barrier()
-        e0.record()
-        if graph is not None:
-            graph.replay()
-        else:
-            for i in range(K):
-                launch(i)
-        e1.record()
-        barrier()
-        times.append(e0.elapsed_time(e1))
-    ms_total = sorted(times)[len(times) // 2]      # median repetition of the K-step region
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    res = time_workload(name, dev, 1234 + 17 * rank, K, W, reps, world, barrier, not args.no_graph)
+    sets, fem, nsets, mode = res["sets"], res["fem"], res["nsets"], res["mode"]
+    t = torch.tensor([res["ms_step"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / K
+    ms_step = float(t.item())
     value = dof_step * world / (ms_step * 1e-3) / 1e9
 
     # ---- e2e: public API, pinned host inputs, H2D + launch + D2H(loss) every step
@@ -402,13 +456,41 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = dof_step * world * Ke / float(te.item()) / 1e9
+    del sets, res, devbuf, host, hs
+    torch.cuda.empty_cache()
+    # ---- the other BASELINE configs and the north_star's named roofline points, measured the same way
+    points = None
+    if world == 1 and args.points and name == DEFAULT:
+        peak0, _ = measured_peak_gbs()
+        points = {}
+        for pn in POINTS:
+            try:
+                r = time_workload(pn, dev, 4321, max(20, min(K, 100)), 5, 3)
+                points[pn] = point_of(pn, r, peak0)
+                del r
+            except Exception as e:   # noqa: BLE001  (the headline must still be printed)
+                points[pn] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
     clocks = sampler.stop() if rank == 0 else None
+    if points and clocks and clocks.get("sm_mhz"):
+        for v in points.values():
+            if "secondary" in v:
+                pk = 148 * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12
+                v["secondary"]["peak"], v["secondary"]["frac"] = pk, v["secondary"]["achieved"] / pk
+                v["secondary"]["clock_mhz"] = clocks["sm_mhz"]
     train = None
     if args.train_steps > 0 and name in ("poisson2d_param_256_b64", "poisson3d_param_64_b16"):
         try:
             train = train_step_rate(name, dev, world, rank, args.train_steps, 5)
         except Exception as e:   # noqa: BLE001  (the FEM line must still be printed)
             train = {"error": f"{type(e).__name__}: {e}"}
+    # ---- N > 1: the one path with a real exchange step (256^3 field in z-slabs, peer-memory halos)
+    slab = None
+    if world > 1 and args.slab and name == DEFAULT:
+        try:
+            slab = slab_measure(args, world, rank, dev, steps=max(20, min(K, 100)))
+        except Exception as e:   # noqa: BLE001
+            slab = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -429,27 +511,38 @@ def run_ours(args):
                                 "best of 5 -- a baseline, not the product path"}
                 except Exception as e:   # noqa: BLE001
                     cpu["same_path_on_this_gpu"] = {"error": f"{type(e).__name__}: {e}"}
+        tr = measured_traffic(name) or {}
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = 148 * 128 * 2 * mhz * 1e6 / 1e12
         line = {
             "metric": "FEM loss+grad throughput", "value": value, "unit": "GDOF/s", "n_gpus": world,
             "steps": K, "warmup": max(W, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "desc": desc, "batch_per_gpu": B, "grid": [size] * nsd,
-                       "dof_per_step_per_gpu": dof_step, "launch": mode,
-                       "l2": f"inputs rotated over {nsets} buffer sets ({nsets * step_bytes / 1e6:.0f} MB > 126 MB L2)",
-                       "timing": f"CUDA events around {K} steps, median of {reps} repetitions, max over ranks",
-                       "parallelism": f"dp{world} (batch sharded, no data-path collective)"},
+            "config": shared_config(name, world),
+            "run": {"launch": mode,
+                    "timing": f"CUDA events around {K} steps, median of {reps} repetitions, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": (measured_traffic(name) or {}).get("bytes"),
-                         "traffic_source": (measured_traffic(name) or {}).get("source"),
+                         "frac": achieved / peak, "traffic": tr.get("bytes"),
+                         "traffic_read": tr.get("dram_read"), "traffic_write": tr.get("dram_write"),
+                         "traffic_note": tr.get("note"), "traffic_source": tr.get("source"),
                          "peak_source": peak_src, "bytes_per_dof": bpd,
                          "algorithmic_bytes_per_launch": step_bytes,
-                         "kernel": "k_fem2d_tma" if nsd == 2 else "k_fem3d_tma"},
+                         "kernel": "k_fem2d_tma" if nsd == 2 else "k_fem3d_tma",
+                         "secondary": {"bound": "fp32_pipe", "unit": "TFLOP/s",
+                                       "achieved": value / world * FLOPS_PER_DOF[nsd] / 1e3, "peak": fp32_peak,
+                                       "frac": value / world * FLOPS_PER_DOF[nsd] / 1e3 / fp32_peak,
+                                       "algorithmic_flops_per_dof": FLOPS_PER_DOF[nsd],
+                                       "note": "148 SMs x 128 lanes x 2 x the SM clock under load; 3-D is bound here "
+                                               "(register-operand dispatch), 2-D by HBM"}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": Ke, "note": "pinned host -> device copy of all input fields + fused launch + loss.item() every step; CUDA events around the steps, max over ranks"},
+                    "steps": Ke, "h2d_gbs_per_gpu": h2d * Ke / float(te.item()) / 1e9,
+                    "note": "pinned host -> device copy of all input fields + fused launch + loss.item() every step; CUDA events around the steps, max over ranks"},
             "gpu_launches": K,
             "clocks": clocks,
             "train": train,
+            "points": points,
+            "slab": slab,
         }
         print(json.dumps(line))
     if world > 1:
@@ -514,23 +607,16 @@ def train_step_rate(name, dev, world, rank, steps, warmup):
 
 
 # ------------------------------------------------------------------------------------ z-slab arm
-def run_slab(args):
-    """One 256^3 field over all ranks: per step = halo exchange of u (NCCL
-    send/recv) + fused kernel on the slab + scalar loss all-reduce.  Strong scaling."""
+def slab_measure(args, world, rank, dev, steps=None, workload="poisson3d_256_slab"):
+    """One 256^3 field over all ranks: per step = halo exchange of u + fused kernel on
+    the slab + scalar loss all-reduce.  Strong scaling.  Needs an initialised process group when
+    world > 1.  Returns the result dict on rank 0 (None elsewhere), including a bit-exactness check
+    of the loss against the single-kernel value where that is cheap (world == 1 trivially true)."""
     import torch
     import torch.distributed as dist
     from diffnet_b200 import ops
     from diffnet_b200.slab import ZSlabPoisson3D, make_slab
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    name = args.workload
-    nsd, N, _, bpd, desc = WORKLOADS[name]
+    nsd, N, _, bpd, desc = WORKLOADS[workload]
     h = 1.0 / (N - 1)
     geom = ops.Geometry(3, N, N, N, h, h, h, 2)
     sp = ZSlabPoisson3D(geom, transport=args.transport)
@@ -546,7 +632,7 @@ def run_slab(args):
     us = [torch.randn(nl, N, N, device=dev, generator=g) for _ in range(nsets)]
     sp.set_fields(nu=inside, f=torch.full_like(inside, 500.0), dirichlet=[(1.0 - inside, 0.0)],
                   already_local=True, c_k=0.5)
-    K, W = args.steps, max(args.warmup, 3)
+    K, W = steps or args.steps, max(args.warmup, 3)
 
     kw = dict(zero_halo_grad=False, overlap=args.overlap)
     mode = "eager"
@@ -582,22 +668,63 @@ def run_slab(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / K
     dof = N ** 3
+    # exchange alone (put + wait of both halo planes), same launch path, for the step's timeline
+    xms = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for i in range(20):
+            sp.exchange_halos(us[i % nsets])
+        e1.record()
+        torch.cuda.synchronize()
+        tx = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        xms = float(tx.item()) / 20
+    timed_out = bool(sp._peer_halo.timed_out()) if getattr(sp, "_peer_halo", None) is not None else False
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak_gbs()
+    value = dof / (ms * 1e-3) / 1e9
+    achieved = dof * bpd / (ms * 1e-3) / 1e9 / world
+    return {"workload": workload, "desc": desc, "value": value, "unit": "GDOF/s", "n_gpus": world, "scaling": "strong",
+            "ms_per_step": ms, "steps": K, "exchange_ms_eager": xms, "slab_planes_rank0": nl, "launch": mode,
+            "transport": ("NVLink peer-memory put/wait kernels (CUDA IPC)" if args.transport == "peer"
+                          else "ncclSend/Recv") + (" overlapped with the interior planes" if args.overlap else ""),
+            "nvlink_bytes_per_step_per_rank": (2 if world > 1 else 0) * N * N * 4,
+            "roofline_per_gpu": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                 "frac": achieved / peak, "bytes_per_dof": bpd, "kernel": "k_fem3d_tma"},
+            "loss": float(loss), "device_wait_timed_out": timed_out,
+            "l2": f"{nsets} rotating slabs x {nl * N * N * bpd / 1e6:.0f} MB per rank (static fields shared)"}
+
+
+def run_slab(args):
+    """--workload poisson3d_256_slab: the z-slab arm on its own (one JSON line)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    r = slab_measure(args, world, rank, dev)
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        value = dof / (ms * 1e-3) / 1e9
-        achieved = dof * bpd / (ms * 1e-3) / 1e9 / world
+        name = args.workload
         print(json.dumps({
-            "metric": "FEM loss+grad throughput", "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "desc": desc, "grid": [N, N, N], "slab_planes_rank0": nl,
-                       "launch": mode, "l2": f"{nsets} rotating slabs x {nl * N * N * bpd / 1e6:.0f} MB per rank (static fields shared)",
-                       "timing": f"CUDA events around {K} steps, max over ranks",
-                       "parallelism": f"z-slab x{world}: " + ("NVLink peer-memory put/wait kernels (CUDA IPC)" if args.transport == "peer" else "ncclSend/Recv") + " for the 2 halo planes" + (" overlapped with the interior planes" if args.overlap else "") + " + loss all-reduce per step"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_dof": bpd, "kernel": "k_fem3d_tma",
-                         "note": "per-GPU: algorithmic bytes of the rank's owned planes / step time"},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": None, "loss": float(loss)}))
+            "metric": "FEM loss+grad throughput", "value": r["value"], "unit": "GDOF/s", "n_gpus": world,
+            "steps": r["steps"], "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "desc": r["desc"], "grid": [256, 256, 256],
+                       "slab_planes_rank0": r["slab_planes_rank0"], "launch": r["launch"], "l2": r["l2"],
+                       "timing": f"CUDA events around {r['steps']} steps, max over ranks",
+                       "parallelism": f"z-slab x{world}: {r['transport']} for the 2 halo planes + loss all-reduce per step"},
+            "roofline": dict(r["roofline_per_gpu"], traffic=None,
+                             note="per-GPU: algorithmic bytes of the rank's owned planes / step time"),
+            "cpu_baseline": None, "e2e": None, "gpu_launches": r["steps"], "clocks": None, "loss": r["loss"],
+            "slab": r}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -616,6 +743,10 @@ def main():
                     help="z-slab arm: halo transport (our NVLink peer-memory kernels, or NCCL send/recv)")
     ap.add_argument("--overlap", action="store_true",
                     help="z-slab arm: interior planes while the halos are in flight (3 launches instead of 1)")
+    ap.add_argument("--no-points", dest="points", action="store_false",
+                    help="skip the extra BASELINE configs / roofline points reported under `points` (N = 1)")
+    ap.add_argument("--no-slab", dest="slab", action="store_false",
+                    help="skip the 256^3 z-slab arm reported under `slab` (N > 1)")
     ap.add_argument("--train-steps", type=int, default=20,
                     help="also time this many full training steps (UNet + loss + DDP + Adam); 0 = skip")
     args = ap.parse_args()
