@@ -244,6 +244,17 @@ class PreparedEnergy:
         nuc = _canon(nu, geom, "nu") if nu is not None else None
         fc = _canon(f, geom, "f") if f is not None else None
         nzm = _canon(nu_zero_mask, geom, "nu_zero_mask") if nu_zero_mask is not None else None
+        # the call is bound to STORAGE: a tensor that had to be copied (dtype conversion, x not
+        # contiguous) would be read from a stale private copy on every later call
+        bound = [("u", u, uc), ("nu", nu, nuc), ("f", f, fc), ("nu_zero_mask", nu_zero_mask, nzm)]
+        bound += [(f"dirichlet[{i}].mask", m, _canon(m, geom, "mask")) for i, (m, _) in enumerate(dirichlet)]
+        bound += [(f"dirichlet[{i}].value", v, _canon(v, geom, "value")) for i, (_, v) in enumerate(dirichlet)
+                  if torch.is_tensor(v)]
+        for nm, orig, canon in bound:
+            if orig is not None and canon.data_ptr() != orig.data_ptr():
+                raise L.DiffNetFEMError(
+                    f"prepare_energy: {nm} would have to be copied (dtype {orig.dtype}, strides {tuple(orig.stride())}); "
+                    "a prepared call binds storage -- pass float32 tensors whose x axis is contiguous")
         fg = None
         if f_gp is not None:
             _require_cuda(f_gp, "f_gp")
@@ -251,7 +262,8 @@ class PreparedEnergy:
             fg = f_gp if f_gp.dim() == geom.nsd + 2 else f_gp.unsqueeze(0)
             if tuple(fg.shape[1:]) != (ngp,) + geom.elems or fg.dtype != torch.float32:
                 raise L.DiffNetFEMError(f"f_gp must be float32 (B|1, {ngp}, {geom.elems})")
-            fg = fg.contiguous()
+            if not fg.is_contiguous():
+                raise L.DiffNetFEMError("prepare_energy: f_gp must be contiguous (a prepared call binds storage)")
         masks_t = [m for m, _ in dirichlet] + [v for _, v in dirichlet if torch.is_tensor(v)]
         B = _batch_of(uc, nuc, fc, nzm, fg, *[_canon(m, geom, "mask") for m in masks_t])
         self._marr, self._nm = _masks_struct(dirichlet, geom, B, keep)
@@ -345,7 +357,12 @@ class FEMEnergyFunction(torch.autograd.Function):
 
     Forward AND gradient come from the single fused launch in forward(); backward only scales
     (in place, skipped on the device when grad_output == 1).  First-order only
-    (once_differentiable), which is all Adam / LBFGS need."""
+    (once_differentiable), which is all Adam / LBFGS need.
+
+    The gradient buffer is handed to autograd, not copied, and scaling it in place consumes it: a
+    SECOND backward through the same node (``retain_graph=True``, or ``autograd.grad`` followed by
+    ``backward``) raises instead of silently returning ``grad_output**2 * dL/du`` -- re-run the
+    forward (one launch) to differentiate again."""
 
     @staticmethod
     def forward(ctx, u, nu, geom, f, f_gp, dirichlet, nu_zero_mask, c_k, c_f, scale, reduction,
@@ -361,11 +378,17 @@ class FEMEnergyFunction(torch.autograd.Function):
         ctx.nu_ref = nu if need_nu else None
         ctx.save_for_backward(*[t for t in (grad if need_u else None, grad_nu) if t is not None])
         ctx.has = (need_u, need_nu)
+        ctx.consumed = False
         return loss
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
+        if ctx.consumed:
+            raise RuntimeError(
+                "FEMEnergyFunction: backward was already run through this node; its gradient buffer was scaled "
+                "in place and handed to autograd.  Evaluate the loss again (one fused launch) for another backward.")
+        ctx.consumed = True
         saved = list(ctx.saved_tensors)
         gu = gnu = None
         if ctx.has[0]:

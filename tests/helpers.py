@@ -12,6 +12,7 @@ from oracle.fem import Q1Oracle
 
 LOSS_RTOL = 1e-5
 GRAD_RTOL = 1e-4
+GRAD_MAX_RTOL = 1e-4     # max |g - g_ref| / max |g_ref|: a handful of wrong seam nodes cannot hide in an L2 norm
 
 
 def oracle_for(fem, dtype=torch.float64):
@@ -55,6 +56,9 @@ def assert_parity(loss, grad, loss_ref, grad_ref, masks=(), what=""):
     el, eg = rel_scalar(loss, loss_ref), rel_l2(grad, grad_ref.reshape(grad.shape))
     assert el <= LOSS_RTOL, f"{what}: loss rel err {el:.3e} (got {float(loss)}, want {float(loss_ref)})"
     assert eg <= GRAD_RTOL, f"{what}: grad rel-L2 err {eg:.3e}"
+    gr = grad_ref.reshape(grad.shape).double()
+    em = float((grad.double() - gr).abs().max() / gr.abs().max().clamp_min(1e-300))
+    assert em <= GRAD_MAX_RTOL, f"{what}: grad max-norm err {em:.3e}"
     for m in masks:
         m = torch.as_tensor(m).detach().cpu()
         if grad.dim() == m.dim():

@@ -3,6 +3,7 @@
 Tolerances (north_star): loss rel <= 1e-5, gradient rel-L2 <= 1e-4, gradient exactly 0 on
 Dirichlet nodes.  The oracle truth is evaluated in fp64 on the CPU.
 """
+import math
 import os
 
 import numpy as np
@@ -316,6 +317,29 @@ def test_baseline_grids_against_oracle(B, N):
     loss, grad = run_energy(fem, u, **kw)
     lref, gref = oracle_energy(fem, u, **kw)
     assert_parity(loss, grad, lref, gref, masks=(bc1, bc2), what=f"E1 {B}x{N}x{N}")
+
+
+@pytest.mark.parametrize("B,N,samples", [(64, 256, (0, 31, 63)), (16, 512, (0, 7, 15))])
+def test_bench_launch_shapes_against_oracle(B, N, samples):
+    """The launch shapes the bench times (256^2 x 64: one wave of short row chunks; 512^2 x 16), not a
+    small-batch stand-in: the launch plan depends on B, samples are independent, so three samples of
+    the full-batch launch are compared with the fp64 oracle run on those samples alone."""
+    from diffnet_b200.synthetic import poisson2d_parametric_batch
+    fem = DiffNet2DFEM(None, domain_size=N, batch_size=B)
+    u, inputs, f = poisson2d_parametric_batch(B, N, DEV, seed=B + N)
+    kw = dict(nu=inputs[:, 0:1], f=f, dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)])
+    loss, grad = fem.energy_loss_and_grad(u, reduction="sum", **kw)
+    tot = 0.0
+    for b in samples:
+        sl = slice(b, b + 1)
+        kwb = dict(nu=inputs[sl, 0:1], f=f[sl], dirichlet=[(inputs[sl, 1:2], 1.0), (inputs[sl, 2:3], 0.0)])
+        lref, gref = oracle_energy(fem, u[sl], reduction="sum", **kwb)
+        lb, gb = fem.energy_loss_and_grad(u[sl], reduction="sum", **kwb)      # B = 1 launch of the same sample
+        assert_parity(lb, grad[b], lref, gref[0, 0], masks=(inputs[b, 1], inputs[b, 2]),
+                      what=f"sample {b} of the B={B} launch at {N}^2")
+        assert torch.equal(gb[0], grad[b])                                    # seams are exact: plans agree bit for bit
+        tot += float(lref)
+    assert math.isfinite(float(loss))
 
 
 def test_immersed_geometry_masks():

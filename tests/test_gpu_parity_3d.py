@@ -178,6 +178,23 @@ def test_baseline_grids_against_oracle(N):
     assert_parity(loss, grad, lref, gref, masks=(src, sink), what=f"3D {N}^3")
 
 
+def test_bench_launch_shape_64cubed_batch16_against_oracle():
+    """configs[2] as the bench launches it (64^3, B = 16, nu == 1, source/sink masks): one sample of the
+    full-batch launch against the fp64 oracle on that sample."""
+    from diffnet_b200.synthetic import poisson3d_parametric_batch
+    B, N, b = 16, 64, 11
+    fem = DiffNet3DFEM(None, domain_size=N, batch_size=B)
+    u, src, sink, f = poisson3d_parametric_batch(B, N, DEV, seed=5)
+    f = f + torch.randn_like(f)
+    loss, grad = fem.energy_loss_and_grad(u, f=f, dirichlet=[(sink, 0.0), (src, 1.0)], reduction="sum")
+    sl = slice(b, b + 1)
+    kwb = dict(f=f[sl], dirichlet=[(sink[sl], 0.0), (src[sl], 1.0)])
+    lref, gref = oracle_energy(fem, u[sl], reduction="sum", **kwb)
+    lb, gb = fem.energy_loss_and_grad(u[sl], reduction="sum", **kwb)
+    assert_parity(lb, grad[b], lref, gref[0, 0], masks=(sink[b, 0], src[b, 0]), what="sample 11 of the 64^3 x 16 launch")
+    assert rel_l2(gb[0], grad[b]) < 2e-6
+
+
 def test_streaming_and_tile_paths_agree():
     """k_fem3d_tma (bulk-async streaming) vs k_fem3d (general tile kernel): same operator."""
     B, D, H, W = 2, 19, 37, 72
