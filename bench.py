@@ -633,8 +633,38 @@ def slab_measure(args, world, rank, dev, steps=None, workload="poisson3d_256_sla
     sp.set_fields(nu=inside, f=torch.full_like(inside, 500.0), dirichlet=[(1.0 - inside, 0.0)],
                   already_local=True, c_k=0.5)
     K, W = steps or args.steps, max(args.warmup, 3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    kw = dict(zero_halo_grad=False, overlap=args.overlap)
+    def timed(step):
+        for i in range(W):
+            step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(K):
+            out = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / K, out
+
+    # (1) the linked step: ONE launch per rank (puts + flag waits + FEM kernel + loss push), graph-replayed
+    linked_ms, linked_mode, loss_linked = None, None, None
+    if world > 1 and args.transport == "peer":
+        try:
+            rp = sp.capture(us, linked=True) if not args.no_graph else None
+            linked_mode = "cuda_graph (one linked launch per step)" if rp is not None else "eager (one linked launch per step)"
+            linked_ms, _ = timed((lambda i: rp()) if rp is not None else (lambda i: sp.step_linked(us[i % nsets])))
+            loss_linked = float(sp.global_loss())
+        except Exception as e:   # noqa: BLE001
+            linked_mode = f"failed: {type(e).__name__}: {e}"
+            torch.cuda.synchronize()
+    # (2) separate launches: halo put/wait kernels (or NCCL) + FEM kernel + peer all-reduce of the loss
+    kw = dict(zero_halo_grad=False, overlap=args.overlap and args.transport != "peer")
     mode = "eager"
     replays = None
     # NCCL point-to-point inside a captured graph hung on this stack: graphs need the peer transport for N > 1
@@ -645,28 +675,9 @@ def slab_measure(args, world, rank, dev, steps=None, workload="poisson3d_256_sla
         except Exception as e:   # noqa: BLE001
             replays, mode = None, f"eager (graph capture failed: {type(e).__name__}: {e})"
             torch.cuda.synchronize()
-
-    def step(i):
-        if replays is not None:
-            return replays()
-        return sp.loss_and_grad(us[i % nsets], **kw)
-
-    for i in range(W):
-        step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(K):
-        loss, grad = step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / K
+    sep_ms, (loss, grad) = timed((lambda i: replays()) if replays is not None
+                                 else (lambda i: sp.loss_and_grad(us[i % nsets], **kw)))
+    ms = linked_ms if linked_ms is not None else sep_ms
     dof = N ** 3
     # exchange alone (put + wait of both halo planes), same launch path, for the step's timeline
     xms = None
@@ -681,6 +692,19 @@ def slab_measure(args, world, rank, dev, steps=None, workload="poisson3d_256_sla
         tx = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         dist.all_reduce(tx, op=dist.ReduceOp.MAX)
         xms = float(tx.item()) / 20
+    # the two paths on the SAME slab: global loss (different summation of the partials: tolerance) and
+    # owned gradient (bit for bit)
+    parity_check = None
+    if world > 1 and linked_ms is not None:
+        o0, o1 = sp.slab.own_local
+        l_sep, g_sep = sp.loss_and_grad(us[0], **kw)
+        g_sep = g_sep.clone()
+        _, g_l = sp.step_linked(us[0])
+        l_link = sp.global_loss()
+        eq = torch.tensor([1.0 if torch.equal(g_l[o0:o1], g_sep[o0:o1]) else 0.0], device=dev)
+        dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+        parity_check = {"loss_rel_diff": abs(float(l_link) - float(l_sep)) / max(abs(float(l_sep)), 1e-30),
+                        "owned_grad_bit_equal_all_ranks": bool(eq.item() == 1.0)}
     timed_out = bool(sp._peer_halo.timed_out()) if getattr(sp, "_peer_halo", None) is not None else False
     if rank != 0:
         return None
@@ -688,7 +712,12 @@ def slab_measure(args, world, rank, dev, steps=None, workload="poisson3d_256_sla
     value = dof / (ms * 1e-3) / 1e9
     achieved = dof * bpd / (ms * 1e-3) / 1e9 / world
     return {"workload": workload, "desc": desc, "value": value, "unit": "GDOF/s", "n_gpus": world, "scaling": "strong",
-            "ms_per_step": ms, "steps": K, "exchange_ms_eager": xms, "slab_planes_rank0": nl, "launch": mode,
+            "ms_per_step": ms, "steps": K, "exchange_ms_eager": xms, "slab_planes_rank0": nl,
+            "launch": linked_mode if linked_ms is not None else mode,
+            "separate_launches": {"ms_per_step": sep_ms, "value": dof / (sep_ms * 1e-3) / 1e9, "launch": mode,
+                                  "loss": float(loss)},
+            "linked": {"ms_per_step": linked_ms, "launch": linked_mode, "global_loss": loss_linked,
+                       "vs_separate_launches": parity_check},
             "transport": ("NVLink peer-memory put/wait kernels (CUDA IPC)" if args.transport == "peer"
                           else "ncclSend/Recv") + (" overlapped with the interior planes" if args.overlap else ""),
             "nvlink_bytes_per_step_per_rank": (2 if world > 1 else 0) * N * N * 4,

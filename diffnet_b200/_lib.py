@@ -38,6 +38,13 @@ class dn_consts(C.Structure):
                 ("reduction", C.c_int32), ("_pad", C.c_int32)]
 
 
+class dn_slab_link(C.Structure):
+    _fields_ = [("halo_plane", C.c_void_p * 2), ("halo_flag", C.c_void_p * 2), ("put_dst", C.c_void_p * 2),
+                ("put_flag", C.c_void_p * 2), ("put_plane", C.c_int32 * 2), ("loss_slots", C.c_void_p),
+                ("step", C.c_void_p), ("tickets", C.c_void_p), ("status", C.c_void_p),
+                ("max_spins", C.c_int64), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 _P = C.POINTER
 _ENERGY_ARGS = [_P(dn_field), _P(dn_field), _P(dn_field), _P(dn_field), _P(dn_mask), C.c_int,
                 _P(dn_field), _P(dn_geom), _P(dn_consts), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -56,6 +63,12 @@ PROTOTYPES = {
     "dn_debug_plan": (C.c_int, [_P(dn_geom), C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "dn_fem_energy_2d_f32": (C.c_int, _ENERGY_ARGS),
     "dn_fem_energy_3d_f32": (C.c_int, _ENERGY_ARGS),
+    "dn_fem_energy_3d_linked_f32": (C.c_int, [_P(dn_field), _P(dn_field), _P(dn_field), _P(dn_mask), C.c_int,
+                                              _P(dn_field), _P(dn_geom), _P(dn_consts), _P(dn_slab_link),
+                                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
+    "dn_peer_loss_sum_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "dn_fem_residual_2d_f32": (C.c_int, _RESID_ARGS),
     "dn_fem_residual_3d_f32": (C.c_int, _RESID_ARGS),
     "dn_fem_gp_eval_2d_f32": (C.c_int, _GP_ARGS),

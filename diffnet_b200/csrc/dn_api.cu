@@ -17,6 +17,8 @@ cudaError_t launch_peer_put(float* dst_peer, const float* src, size_t n, int* re
                             unsigned int* ticket, cudaStream_t s);
 cudaError_t launch_peer_wait(float* halo, const float* staged, size_t n, const int* flag, int* expect,
                              long long max_spins, int* status, cudaStream_t s);
+cudaError_t launch_peer_loss_sum(const double* slots, int world, const int* step, long long max_spins, int* status,
+                                 float* out, cudaStream_t s);
 cudaError_t launch_peer_allreduce(const float* partial, float* out, double* slots, double* const* peer_slots,
                                   int rank, int world, int* counter, long long max_spins, int* status,
                                   cudaStream_t s);
@@ -436,6 +438,40 @@ int dn_fem_energy_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* 
                        c->scale / count, 3, &cm)) return rc;
   return run3d(cm.u, cm.nu, cm.f, cm.fgp, cm.numask, cm.mk, cm.MK, cm.k, cm.rule, cm.vec4, g,
                grad_u, 0, 1, workspace, workspace_bytes, loss_out, loss_out_f32, stream, sms);
+}
+
+int dn_fem_energy_3d_linked_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                                const dn_mask* masks, int nmasks, const dn_field* nu_zero_mask,
+                                const dn_geom* g, const dn_consts* c, const dn_slab_link* link,
+                                float* grad_u, void* workspace, size_t workspace_bytes,
+                                double* loss_out, float* loss_out_f32, void* stream) {
+  int sms = 0;
+  if (int rc = device_ok(&sms)) return rc;
+  if (!c || !g || !link) return fail(DN_EINVAL, "consts / geom / link is NULL");
+  double count = 1.0;
+  if (c->reduction == 0) {
+    long long nelz = g->nz - 1;
+    if (g->z_own_hi > g->z_own_lo) {
+      const int hi = g->z_own_hi < g->nz - 1 ? g->z_own_hi : g->nz - 1;
+      nelz = hi - g->z_own_lo;
+    }
+    count = g->mean_count > 0 ? g->mean_count
+                              : (double)g->batch * (g->nx - 1) * (double)(g->ny - 1) * (double)nelz;
+  }
+  Common cm;
+  if (int rc = prepare(u, nu, f, nullptr, masks, nmasks, nu_zero_mask, g, c->c_k, c->c_f,
+                       c->scale / count, 3, &cm)) return rc;
+  return run3d(cm.u, cm.nu, cm.f, cm.fgp, cm.numask, cm.mk, cm.MK, cm.k, cm.rule, cm.vec4, g,
+               grad_u, 0, 1, workspace, workspace_bytes, loss_out, loss_out_f32, stream, sms, link);
+}
+
+int dn_peer_loss_sum_f32(const double* slots, int world, const int32_t* step, int64_t max_spins,
+                         int32_t* status, float* out, void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!slots || !step || !status || !out) return fail(DN_EINVAL, "NULL pointer");
+  if (world < 1 || world > 32) return fail(DN_EINVAL, "world %d (1..32)", world);
+  return check_cuda(launch_peer_loss_sum(slots, world, step, max_spins > 0 ? max_spins : (1LL << 26), status, out,
+                                         (cudaStream_t)stream), "peer_loss_sum launch");
 }
 
 int dn_fem_residual_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* f,

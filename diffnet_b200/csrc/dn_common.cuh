@@ -28,6 +28,12 @@ struct Reduce {
   unsigned int* counter; // zero on entry, zero on exit
   double* loss_out;      // nullable
   float* loss_f32;       // nullable
+  // linked z-slab launches (dn_slab_link): the rank's total is also stored into slot `rank` of every
+  // rank's receive area (double[world] + int32[world] flags, peer-mapped) and the launch counter is
+  // advanced -- the all-reduce of the loss without a collective launch.  All null/0 otherwise.
+  double* const* peer_slots;
+  int* step;             // this rank's launch counter of the current parity (device word)
+  int rank, world;
 };
 
 // Folded constants of the closed-form Q1 energy (DESIGN.md "element math"):

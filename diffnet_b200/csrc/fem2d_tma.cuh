@@ -281,6 +281,17 @@ __device__ __forceinline__ void finish_loss_w0(const Reduce& r, double cta_value
     for (int q = 0; q < 40; ++q) s += v[q];
   }
   s = warp_sum(s);
+  if (r.peer_slots) {      // linked z-slab launch: push the rank total to every rank (NVLink stores), then the flags
+    const int want = *r.step + 1;
+    if (lane < r.world) {
+      double* slots = r.peer_slots[lane];
+      *reinterpret_cast<volatile double*>(slots + r.rank) = s;
+      __threadfence_system();
+      *reinterpret_cast<volatile int*>(reinterpret_cast<int*>(slots + r.world) + r.rank) = want;
+    }
+    __syncwarp();
+    if (lane == 0) *r.step = want;
+  }
   if (lane == 0) {
     if (r.loss_out) *r.loss_out = s;
     if (r.loss_f32) *r.loss_f32 = (float)s;

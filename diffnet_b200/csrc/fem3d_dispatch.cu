@@ -10,7 +10,7 @@ long long plan3t_max_ctas(const dn_geom* g);
 int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, const Field& numask,
           const Mask* mk, int nmasks, int MK, const Consts& k, bool vec4, const dn_geom* g, float* grad,
           int mode, int mask_input, void* workspace, size_t wsb, double* loss_out, float* loss_f32,
-          void* stream, int sms, bool* handled);
+          void* stream, int sms, bool* handled, const dn_slab_link* link);
 }
 
 namespace dn {
@@ -87,13 +87,14 @@ long long plan3d_max_ctas(const dn_geom* g) {
 int run3d(const Field& u, const Field& nu, const Field& f, const Field& fgp, const Field& numask,
           const Mask* mk, int MK, const Consts& k, const Rule& rule, bool vec4, const dn_geom* g,
           float* grad, int mode, int mask_input, void* workspace, size_t wsb, double* loss_out,
-          float* loss_f32, void* stream, int sms) {
+          float* loss_f32, void* stream, int sms, const dn_slab_link* link) {
   {   // streaming path: common aligned cases (the rest stays on k_fem3d)
     bool handled = false;
     const int nmasks = (MK == 4) ? 1 : MK;
     int rc = run3t(u, nu, f, fgp, numask, mk, nmasks, MK, k, vec4, g, grad, mode, mask_input, workspace,
-                   wsb, loss_out, loss_f32, stream, sms, &handled);
+                   wsb, loss_out, loss_f32, stream, sms, &handled, link);
     if (rc != DN_OK || handled) return rc;
+    if (link) return fail(DN_EINVAL, "a linked z-slab launch needs the streaming path (nx %% 4 == 0, aligned x-contiguous fields)");
   }
   vec4 = vec4 && ((uintptr_t)grad % 16 == 0);
   Plan3D pl = plan3d(g, vec4, sms);

@@ -49,6 +49,21 @@ struct K3 {
   float kscale;
 };
 
+// Linked z-slab launch (include/diffnet_fem.h: dn_slab_link): the halo exchange of u and the loss
+// all-reduce ride inside the FEM launch.  nput == 0: not linked.
+struct Link3 {
+  CUtensorMap tmh[2];           // (x, y, 1, 1) maps over the staged halo planes [below, above]
+  const int* hflag[2];          // local flag words the neighbours release; null = no neighbour on that side
+  float4* pdst[2];              // neighbour's staging plane (peer-mapped); null = none
+  const float4* psrc[2];        // my first / last owned plane of u
+  int* pflag[2];                // neighbour's flag word (peer-mapped)
+  long long pn4;                // float4 per plane
+  int nput;                     // CTAs that copy one side's plane (the launch is 2 * nput CTAs larger)
+  unsigned int* tickets;        // [2] zero-initialised scratch
+  int* status;                  // set to 1 if a device-side wait ran out of polls
+  long long max_spins;
+};
+
 struct P3T {
   CUtensorMap tm[DN_T2_MAXF];   // one 4-D (x, y, z, b) tiled map per field; slot order: u, [nu], [f], [numask], masks..., [value field]
   int bmul[DN_T2_MAXF];         // 1: the field has a batch dimension, 0: broadcast over the batch
@@ -64,6 +79,7 @@ struct P3T {
   float* grad;                  // dense (B, nz, ny, nx); nullable
   Reduce red;
   int mode;                     // 0: loss = energy; 1: loss = sum(out^2)
+  Link3 lk;
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
@@ -325,8 +341,38 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats);      // [S] + 1: the layer barrier
   float* const xbuf = reinterpret_cast<float*>(full + S + 1);                               // [2][kXParity]
 
+  // ---- linked z-slab launch: the first 2 * nput CTAs push this rank's boundary planes of u into the
+  // neighbours' staging buffers (plain vectorised stores over NVLink), release the neighbours' flag
+  // words (system scope, last CTA of a side through a ticket) and are done
+  const int nputc = 2 * p.lk.nput;
+  int want = 0;
+  if (nputc) {
+    pdl_wait();
+    want = *p.red.step + 1;
+    if ((int)blockIdx.x < nputc) {
+      const int side = (int)blockIdx.x / p.lk.nput, part = (int)blockIdx.x - side * p.lk.nput;
+      if (p.lk.pdst[side]) {
+        float4* dst = p.lk.pdst[side];
+        const float4* src = p.lk.psrc[side];
+        for (long long i = (long long)part * NT + tid; i < p.lk.pn4; i += (long long)p.lk.nput * NT) dst[i] = src[i];
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+          const unsigned int t = atomicAdd(p.lk.tickets + side, 1u);
+          if (t == (unsigned)p.lk.nput - 1) {          // every CTA of this side has fenced its stores
+            p.lk.tickets[side] = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile int*>(p.lk.pflag[side]) = want;
+          }
+        }
+      }
+      finish_loss_w0(p.red, 0.0);
+      return;
+    }
+  }
+
   // ---- work item: (b, z-chunk, y-tile, x-tile)
-  int w_ = blockIdx.x;
+  int w_ = (int)blockIdx.x - nputc;
   const int itx = w_ % p.ntx; w_ /= p.ntx;
   const int ity = w_ % p.nty; w_ /= p.nty;
   const int izc = w_ % p.nzc;
@@ -352,9 +398,27 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
       uint64_t* bar = full + ist;
       float* dst = ring + ist * stage_floats;
       mbar_arrive_expect_tx(bar, (uint32_t)(NF * BX * p.BY * 4));
+      const int zpl = zf + issued;
+      // linked z-slab launch: the halo planes of u come from the staging buffers the neighbours fill;
+      // only the CTAs whose chunk touches them wait (bounded) for this step's flag
+      const int hs = nputc ? ((zpl == 0 && p.lk.hflag[0]) ? 0 : ((zpl == p.nz - 1 && p.lk.hflag[1]) ? 1 : -1)) : -1;
+      if (hs >= 0) {
+        long long spins = 0;
+        int seen;
+        do {
+          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.lk.hflag[hs]) : "memory");
+          if (seen >= want) break;
+          __nanosleep(32);
+        } while (++spins < p.lk.max_spins);
+        if (seen < want) *p.lk.status = 1;
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        tma_load_4d(dst, &p.lk.tmh[hs], xs, jf, 0, 0, bar);
+      } else {
+        tma_load_4d(dst, &p.tm[0], xs, jf, zpl, b * p.bmul[0], bar);
+      }
 #pragma unroll
-      for (int f = 0; f < NF; ++f)
-        tma_load_4d(dst + f * fstride, &p.tm[f], xs, jf, zf + issued, b * p.bmul[f], bar);
+      for (int f = 1; f < NF; ++f)
+        tma_load_4d(dst + f * fstride, &p.tm[f], xs, jf, zpl, b * p.bmul[f], bar);
     }
     ++issued;
     ist = (ist + 1 == S) ? 0 : ist + 1;

@@ -103,7 +103,7 @@ static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_v
   const int lx_forced = env_i3("DN_T3_LX", 0), ty_forced = env_i3("DN_T3_TY", 0), zc_forced = env_i3("DN_T3_ZC", 0);
   int zmin = env_i3("DN_T3_ZCMIN", 4);
   if (zmin < 1) zmin = 1;
-  int S0 = env_i3("DN_T3_STAGES", 3);
+  int S0 = env_i3("DN_T3_STAGES", 4);
   if (S0 < 2) S0 = 2;
   if (S0 > 8) S0 = 8;
   double best_cost = 0.0;
@@ -199,7 +199,7 @@ int debug_plan3t(const dn_geom* g, int nfields, int has_nu, int64_t* out) {
 int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, const Field& numask,
           const Mask* mk, int nmasks, int MK, const Consts& k, bool vec4, const dn_geom* g, float* grad,
           int mode, int mask_input, void* workspace, size_t wsb, double* loss_out, float* loss_f32,
-          void* stream, int sms, bool* handled) {
+          void* stream, int sms, bool* handled, const dn_slab_link* link) {
   *handled = false;
   const char* path = getenv("DN_3D_PATH");
   if (path && !strcmp(path, "tile")) return DN_OK;
@@ -228,6 +228,13 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   Plan3T pl = plan3t(g, nf, sms, occ, DN_T3_MAXT_OF(NU));
   if (!pl.ok) { cudaGetLastError(); return DN_OK; }
   if (pl.grid > 0x7fffffffLL) return DN_OK;
+  int nput = 0;
+  if (link) {
+    nput = env_i3("DN_SLAB_NPUT", 2);
+    if (nput < 1) nput = 1;
+    if (nput > 16) nput = 16;
+    pl.grid += 2 * nput;
+  }
   const size_t need = 64 + 8 * (size_t)pl.grid;
   if (!workspace || wsb < need) return fail(DN_EWORKSPACE, "workspace too small: %zu < %zu", wsb, need);
   if ((uintptr_t)workspace % 16) return fail(DN_EWORKSPACE, "workspace must be 16-byte aligned");
@@ -262,6 +269,43 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   p.red.partials = (double*)((char*)workspace + 64);
   p.red.loss_out = loss_out; p.red.loss_f32 = loss_f32;
   p.mode = mode;
+  if (link) {
+    if (g->batch != 1) return fail(DN_EINVAL, "linked z-slab launches are for one field (batch 1)");
+    if (!link->step || !link->tickets || !link->status) return fail(DN_EINVAL, "dn_slab_link: step / tickets / status missing");
+    dn_geom gp = *g;
+    gp.nz = 1; gp.batch = 1;
+    const long long plane = (long long)g->ny * g->nx;
+    for (int sd = 0; sd < 2; ++sd) {
+      if (link->halo_plane[sd]) {
+        if (!link->halo_flag[sd]) return fail(DN_EINVAL, "dn_slab_link: halo_flag[%d] missing", sd);
+        Field hf;
+        hf.p = link->halo_plane[sd]; hf.sb = plane; hf.sz = plane; hf.sy = g->nx;
+        int bm = 0;
+        if (!make_map(&p.lk.tmh[sd], hf, &gp, pl.BX, pl.BY, &bm))
+          return fail(DN_EINVAL, "dn_slab_link: halo_plane[%d] is not TMA-addressable (16-byte alignment)", sd);
+        p.lk.hflag[sd] = link->halo_flag[sd];
+      }
+      if (link->put_dst[sd]) {
+        if (!link->put_flag[sd] || link->put_plane[sd] < 0 || link->put_plane[sd] >= g->nz)
+          return fail(DN_EINVAL, "dn_slab_link: put_flag / put_plane[%d] invalid", sd);
+        if (u.sy != g->nx || u.sz != plane || plane % 4 || ((uintptr_t)u.p % 16) || ((uintptr_t)link->put_dst[sd] % 16))
+          return fail(DN_EINVAL, "dn_slab_link: u must be a contiguous, 16-byte aligned slab (ny*nx %% 4 == 0)");
+        p.lk.pdst[sd] = (float4*)link->put_dst[sd];
+        p.lk.psrc[sd] = (const float4*)(u.p + (long long)link->put_plane[sd] * plane);
+        p.lk.pflag[sd] = link->put_flag[sd];
+      }
+    }
+    p.lk.pn4 = plane / 4;
+    p.lk.nput = nput;
+    p.lk.tickets = link->tickets;
+    p.lk.status = link->status;
+    p.lk.max_spins = link->max_spins > 0 ? link->max_spins : (1LL << 26);
+    p.red.step = link->step;
+    p.red.peer_slots = link->loss_slots;
+    p.red.rank = link->rank; p.red.world = link->world;
+    if (link->loss_slots && (link->world < 1 || link->world > 32 || link->rank < 0 || link->rank >= link->world))
+      return fail(DN_EINVAL, "dn_slab_link: rank %d / world %d (world <= 32)", link->rank, link->world);
+  }
   if (env_i3("DN_DEBUG_PLAN", 0))
     fprintf(stderr, "[plan3t] B=%d n=(%d,%d,%d) LXT=%d LXo=%d hl=%d ntx=%d rows=%d TY=%d nty=%d ZC=%d nzc=%d S=%d BX=%d BY=%d "
             "fstride=%d threads=%d grid=%lld smem=%zu\n", g->batch, g->nx, g->ny, g->nz, pl.LXT, pl.LXo, pl.hl, pl.ntx,

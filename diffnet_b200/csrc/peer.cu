@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(256) k_peer_put(float4* __restrict__ dst, cons
 
 // status: 0 = ok; on time-out the kernel writes 1 there and still copies (the caller checks it
 // when it next synchronises) -- a lost neighbour must not hang the GPU.
-__global__ void __launch_bounds__(256) k_peer_wait(float4* __restrict__ halo, const float4* __restrict__ staged,
+// `staged` is written by the remote GPU while this kernel may already be resident: it is read with
+// L2-coherent loads (__ldcg), never through the non-coherent path a const __restrict__ pointer allows.
+__global__ void __launch_bounds__(256) k_peer_wait(float4* __restrict__ halo, const float4* staged,
                                                    long long n4, const int* flag, int* expect,
                                                    long long max_spins, int* status) {
   __shared__ int want;
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(256) k_peer_wait(float4* __restrict__ halo, co
   }
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) halo[i] = staged[i];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) halo[i] = __ldcg(staged + i);
   // the LAST block to finish bumps the expectation (same ticket idea, on the status word's neighbour)
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -93,6 +95,35 @@ __global__ void __launch_bounds__(32) k_peer_allreduce(const float* __restrict__
     *out = (float)s;
     *counter = step;
   }
+}
+
+// Sum of the loss slots a linked z-slab launch filled (fem3d_tma.cuh / finish_loss_w0): waits (bounded) until
+// every rank's flag has reached this rank's launch counter, then adds the doubles in rank order.
+__global__ void __launch_bounds__(32) k_peer_loss_sum(const double* slots, int world, const int* step,
+                                                      long long max_spins, int* status, float* out) {
+  const int t = threadIdx.x;
+  const int want = *step;                       // launches completed on this rank with this parity
+  const int* flags = reinterpret_cast<const int*>(slots + world);
+  if (t < world) {
+    long long spins = 0;
+    while (*reinterpret_cast<const volatile int*>(flags + t) < want) {
+      if (++spins > max_spins) { *status = 1; break; }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (t == 0) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += *reinterpret_cast<const volatile double*>(slots + r);
+    *out = (float)s;
+  }
+}
+
+cudaError_t launch_peer_loss_sum(const double* slots, int world, const int* step, long long max_spins, int* status,
+                                 float* out, cudaStream_t s) {
+  k_peer_loss_sum<<<1, 32, 0, s>>>(slots, world, step, max_spins, status, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_peer_allreduce(const float* partial, float* out, double* slots, double* const* peer_slots,

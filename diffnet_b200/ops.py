@@ -235,9 +235,14 @@ class PreparedEnergy:
     (pointers, not values, are captured); re-prepare if a tensor is reallocated."""
 
     def __init__(self, geom: Geometry, u, nu=None, f=None, f_gp=None, dirichlet=(), nu_zero_mask=None,
-                 c_k=1.0, c_f=1.0, scale=1.0, reduction="mean", z_own=None, mean_count=0.0):
+                 c_k=1.0, c_f=1.0, scale=1.0, reduction="mean", z_own=None, mean_count=0.0, link=None):
+        """``link``: a ``_lib.dn_slab_link`` (3-D only, see include/diffnet_fem.h) -- the launch then also
+        exchanges the z-halo planes of u with the neighbouring ranks and pushes the loss partial."""
         if reduction not in ("mean", "sum"):
             raise L.DiffNetFEMError("reduction must be 'mean' or 'sum'")
+        if link is not None and (geom.nsd != 3 or f_gp is not None):
+            raise L.DiffNetFEMError("a linked (z-slab) call is 3-D with a nodal source term")
+        self._link = link
         self.geom = geom
         keep = []
         uc = _canon(u, geom, "u")
@@ -292,6 +297,14 @@ class PreparedEnergy:
             if ws is None:
                 ws = self._ws[stream] = _workspace_for(L.lib(), self._g, self.geom, self._B, dev, stream)
             hn, hf, hg, hz = self._has
+            if self._link is not None:
+                rc = L.lib().dn_fem_energy_3d_linked_f32(
+                    C.byref(self._fu), C.byref(self._fnu) if hn else None, C.byref(self._ff) if hf else None,
+                    self._marr, self._nm, C.byref(self._fnz) if hz else None, C.byref(self._g), C.byref(self._cs),
+                    C.byref(self._link), C.c_void_p(self.grad.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                    None, C.c_void_p(self.loss.data_ptr()), C.c_void_p(stream))
+                L.check(rc, "dn_fem_energy_3d_linked_f32")
+                return self.loss, self.grad
             rc = self._fn(C.byref(self._fu), C.byref(self._fnu) if hn else None, C.byref(self._ff) if hf else None,
                           C.byref(self._ffg) if hg else None, self._marr, self._nm,
                           C.byref(self._fnz) if hz else None, C.byref(self._g), C.byref(self._cs),

@@ -114,6 +114,8 @@ class ZSlabPoisson3D:
             raise ValueError("transport must be 'nccl' (send/recv) or 'peer' (NVLink peer memory, CUDA only)")
         self.transport = transport
         self._peer_halo = None                 # PeerHalo, created at the first exchange (needs the device)
+        self._linked = {}                      # prepared linked launches per (storage, parity)
+        self._last_linked_parity = 0
         self.fields = {}
         self.dirichlet: Sequence = ()
         self.consts = {}
@@ -197,6 +199,10 @@ class ZSlabPoisson3D:
         s = self.slab
         o0, o1 = s.own_local
         nl = u_local.shape[0]
+        if overlap and exchange and self.world > 1 and self.transport == "peer":
+            raise NotImplementedError(
+                "overlap=True starts the halos with NCCL point-to-point; with transport='peer' use step_linked(), "
+                "which overlaps the exchange with the interior planes inside one launch")
         if not (overlap and exchange and self.world > 1 and (o1 - o0) >= 4):
             if exchange:
                 self.exchange_halos(u_local)
@@ -227,6 +233,52 @@ class ZSlabPoisson3D:
             loss = self._reduce(loss, u_local)
         return loss, grad
 
+    # ---------------------------------------------------------------- linked (one-launch) step
+    def step_linked(self, u_local: torch.Tensor):
+        """ONE launch per rank: the FEM kernel itself stores this rank's boundary planes of u into the
+        neighbours' staging buffers, waits for theirs only in the CTAs that touch a halo plane (the
+        interior planes run meanwhile), and pushes the rank's loss partial to every rank
+        (``include/diffnet_fem.h: dn_slab_link``).  Returns (this rank's loss PARTIAL, grad) -- the
+        same static tensors on every call with the same storage; ``global_loss()`` adds the partials up
+        when the value is wanted.  The halo planes of ``u_local`` itself are NOT refreshed (the kernel
+        reads the staged planes), and the gradient of the halo planes is a partial sum nobody should
+        use.  Needs transport='peer' and CUDA; with one rank it is the plain fused launch."""
+        if self.world == 1:
+            return self.loss_and_grad(u_local, exchange=False, zero_halo_grad=False, reduce_loss=False)
+        if self.transport != "peer" or not u_local.is_cuda:
+            raise NotImplementedError("step_linked needs transport='peer' on CUDA")
+        if not u_local.is_contiguous():
+            raise ValueError("u_local must be contiguous")
+        if self._peer_halo is None:
+            from .peer import PeerHalo
+            self._peer_halo = PeerHalo(self.slab, self.g.ny, self.g.nx, u_local.device, self.group)
+        ph = self._peer_halo
+        par = ph.link_parity
+        ph.link_parity ^= 1
+        key = (u_local.data_ptr(), tuple(u_local.shape), par)
+        call = self._linked.get(key)
+        if call is None:
+            g = self.g
+            count = float((g.nx - 1) * (g.ny - 1) * (g.nz - 1))
+            o0, o1 = self.slab.own_local
+            call = self._linked[key] = ops.PreparedEnergy(
+                self.geom_local, u_local, z_own=(o0, o1), mean_count=count, dirichlet=self.dirichlet,
+                link=ph.link(u_local, par), **self.fields, **self.consts)
+        self._last_linked_parity = par
+        loss, grad = call()
+        return loss, grad.reshape(u_local.shape)
+
+    def global_loss(self) -> torch.Tensor:
+        """Global loss of the most recent ``step_linked`` (sum of all ranks' partials, rank order)."""
+        if self.world == 1 or self._peer_halo is None:
+            raise RuntimeError("global_loss() follows step_linked() on more than one rank")
+        return self._peer_halo.loss_sum(self._last_linked_parity)
+
+    def check(self) -> None:
+        """Raise if a device-side wait of the peer transport timed out (synchronises)."""
+        if self._peer_halo is not None:
+            self._peer_halo.check()
+
     def _reduce(self, loss, u_local):
         if self.transport == "peer" and loss.is_cuda:
             if self._peer_halo is None:
@@ -238,25 +290,29 @@ class ZSlabPoisson3D:
         return loss
 
     def _parity(self):
-        return self._peer_halo.parity if self._peer_halo is not None else 0
+        """(halo parity, all-reduce parity, linked-step parity) of the peer transport."""
+        ph = self._peer_halo
+        return (ph.parity, ph.red_parity, ph.link_parity) if ph is not None else (0, 0, 0)
 
-    def _set_parity(self, p: int):
-        if self._peer_halo is not None:
-            self._peer_halo.parity = p
-            self._peer_halo.red_parity = p
+    def _set_parity(self, p):
+        ph = self._peer_halo
+        if ph is not None:
+            ph.parity, ph.red_parity, ph.link_parity = p
 
-    def capture(self, u_locals, warmup: int = 4, **kw):
-        """Capture whole steps (halo exchange + kernel(s) + loss all-reduce) into CUDA graphs and
-        return ``replay() -> (loss, grad)`` (static output tensors of the step just replayed).
+    def capture(self, u_locals, warmup: int = 4, linked: bool = False, **kw):
+        """Capture whole steps into CUDA graphs and return ``replay() -> (loss, grad)`` (static output
+        tensors of the step just replayed).  ``linked=False``: halo put/wait launches + FEM kernel +
+        peer all-reduce of the loss; ``linked=True``: the single linked launch of ``step_linked`` (the
+        loss returned is then this rank's partial).
         ``u_locals``: one slab tensor or a list of them (the graphs are bound to their storage and
-        replayed round-robin: rotating input sets for benchmarks).  At these sizes a step is ~10
-        host-launched operations of 10-20 us each around a ~100 us kernel: replaying a graph removes
+        replayed round-robin: rotating input sets for benchmarks).  At these sizes a step is a few
+        host-launched operations of 10-20 us each around a 20-100 us kernel: replaying a graph removes
         the host from the critical path.  Every rank must capture and replay in lockstep.  With
-        world > 1 this needs ``transport="peer"`` (our put/wait/all-reduce kernels are plain
-        launches; the captured NCCL send/recv group hung on this stack: torch 2.11 / NCCL 2.28.9,
-        2 x B200).  The halo double-buffering parity is part of each graph: graph i uses parity
-        i % 2 (an even number of graphs is captured), and replay() keeps the host-side parity in
-        step so that eager calls may be mixed in between."""
+        world > 1 this needs ``transport="peer"`` (our kernels are plain launches; the captured NCCL
+        send/recv group hung on this stack: torch 2.11 / NCCL 2.28.9, 2 x B200).  The double-buffering
+        parities are part of each graph: graph i uses the parities (start + i) % 2 (an even number of
+        graphs is captured), and replay() keeps the host-side parities in step so that eager calls
+        may be mixed in between."""
         us = list(u_locals) if isinstance(u_locals, (list, tuple)) else [u_locals]
         if not all(u.is_cuda for u in us):
             raise ValueError("capture() needs CUDA tensors")
@@ -264,37 +320,46 @@ class ZSlabPoisson3D:
             raise NotImplementedError("graph capture with world > 1 needs transport='peer'")
         reduce_loss = kw.pop("reduce_loss", True)
         dev = us[0].device
+
+        def one(u):
+            if linked:
+                return self.step_linked(u)
+            return self.loss_and_grad(u, reduce_loss=reduce_loss, **kw)
+
         ngraphs = len(us) if (self.world == 1 or len(us) % 2 == 0) else 2 * len(us)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for i in range(2 * max(warmup // 2, 1)):      # allocates workspaces, maps the peers; even count
-                self.loss_and_grad(us[i % len(us)], reduce_loss=reduce_loss, **kw)
+                one(us[i % len(us)])
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         start = self._parity()
+        flip = lambda p, i: tuple((q + i) % 2 for q in p)   # noqa: E731
         graphs, outs = [], []
         for i in range(ngraphs):
-            self._set_parity((start + i) % 2)
+            self._set_parity(flip(start, i))
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
-                outs.append(self.loss_and_grad(us[i % len(us)], reduce_loss=reduce_loss, **kw))
+                outs.append(one(us[i % len(us)]))
             graphs.append(g)
             # the capture ran nothing: run the step for real so that every rank's device-side
             # counters advance exactly as the parity sequence says
             g.replay()
-        self._set_parity((start + ngraphs) % 2)
+        self._set_parity(flip(start, ngraphs))
         torch.cuda.synchronize(dev)
         state = {"i": 0}
 
         def replay():
             i = state["i"]
-            if self.world > 1 and self._parity() != (start + i) % 2:
+            if self.world > 1 and self._parity() != flip(start, i):
                 raise RuntimeError("graph replay out of step with the halo parity (an odd number of eager "
                                    "steps was mixed in); run one more eager step or re-capture")
             graphs[i].replay()
             state["i"] = (i + 1) % ngraphs
-            self._set_parity((start + i + 1) % 2)
+            self._set_parity(flip(start, i + 1))
+            if linked:
+                self._last_linked_parity = flip(start, i)[2]
             return outs[i]
         replay.graphs = graphs
         return replay
@@ -303,6 +368,7 @@ class ZSlabPoisson3D:
         """All ranks' owned planes concatenated in z (for checks / output)."""
         o0, o1 = self.slab.own_local
         mine = u_local[o0:o1].contiguous()
+        self.check()                                 # a host synchronisation point: stale halos must not pass silently
         if self.world == 1:
             return mine
         sizes = [slab_bounds(self.g.nz, self.world, r) for r in range(self.world)]

@@ -140,6 +140,51 @@ int dn_fem_energy_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* 
                          double* loss_out, float* loss_out_f32, void* stream);
 
 /*
+ * Linked z-slab step (3-D, one process per GPU; SURVEY.md 8e -- new functionality, the reference runs
+ * solve_in_object_3d.py:191-200 on one GPU): ONE launch per rank and step does the halo exchange of
+ * u, the fused loss + gradient on the slab and the all-reduce of the loss, over NVLink peer memory:
+ *   - the first CTAs of the launch store this rank's first / last owned plane of u into the
+ *     neighbours' staging planes (put_dst, peer-mapped) and release their flag words (put_flag) with
+ *     the launch number (system scope);
+ *   - the kernel reads local plane 0 / nz-1 of u (the halos) from halo_plane[0] / [1] instead of from
+ *     `u`; only the CTAs whose z-chunk touches a halo plane wait -- on the device, bounded by
+ *     max_spins polls -- until *halo_flag >= launch number; all other CTAs start at once, so the
+ *     exchange overlaps the interior planes;
+ *   - the CTA that finishes the loss reduction stores the rank total into slot `rank` of every
+ *     rank's receive area (loss_slots[r]: double[world] then int32[world] flags) and increments
+ *     *step; dn_peer_loss_sum_f32 adds the slots up (rank order) whenever the value is wanted.
+ * `step` is a device word counting the launches of this link (start at 0); consecutive launches
+ * must alternate between two sets {staging planes, flags, loss areas, step} (parity) so that a rank
+ * one step ahead never overwrites data its neighbour still reads.  Pointers of a missing neighbour
+ * are NULL.  All ranks must launch the same sequence.  Needs the streaming path (nx % 4 == 0,
+ * 16-byte aligned x-contiguous fields, nodal f); DN_EINVAL otherwise.  *status becomes 1 if a wait
+ * ran out of polls (the launch then finishes with stale halos: check it when you synchronise).
+ */
+typedef struct dn_slab_link {
+  const float* halo_plane[2];   /* [below, above] local staging plane, ny*nx floats, 16-byte aligned */
+  const int32_t* halo_flag[2];  /* local flag words released by the neighbours */
+  float* put_dst[2];            /* the neighbours' staging planes (peer-mapped) */
+  int32_t* put_flag[2];         /* the neighbours' flag words (peer-mapped) */
+  int32_t put_plane[2];         /* local plane index of u sent below / above (first / last owned) */
+  double* const* loss_slots;    /* DEVICE array[world] of receive areas as mapped here; NULL = no loss exchange */
+  int32_t* step;                /* local device word: launches so far with this set */
+  uint32_t* tickets;            /* 2 zero-initialised local device words (scratch) */
+  int32_t* status;              /* local device word */
+  int64_t max_spins;
+  int32_t rank, world;
+} dn_slab_link;
+
+int dn_fem_energy_3d_linked_f32(const dn_field* u, const dn_field* nu, const dn_field* f,
+                                const dn_mask* masks, int nmasks, const dn_field* nu_zero_mask,
+                                const dn_geom* g, const dn_consts* c, const dn_slab_link* link,
+                                float* grad_u, void* workspace, size_t workspace_bytes,
+                                double* loss_out, float* loss_out_f32, void* stream);
+/* Sum (rank order, bit-identical everywhere) of the loss slots of launch number `want` once every
+ * rank's flag has reached it (bounded device-side wait); out: device float[1]. */
+int dn_peer_loss_sum_f32(const double* slots, int world, const int32_t* step, int64_t max_spins,
+                         int32_t* status, float* out, void* stream);
+
+/*
  * Assembled residual  R = jac * ( K(nu) u' - F(f) ), zeroed at Dirichlet nodes, and
  * loss = sum(R^2)  (12_klsum.py:80-132).  `residual` (dense (B,nz,ny,nx)) is required: it is
  * what the backward pass consumes.  If apply_masks_to_input == 0 the Dirichlet VALUES are not

@@ -45,15 +45,18 @@ def test_struct_layout_matches_c(tmp_path):
     """sizeof/offsetof of every struct, compiled from the header with gcc."""
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "diffnet_fem.h"\n'
-                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dn_field), sizeof(dn_mask),'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dn_field), sizeof(dn_mask),'
                    ' sizeof(dn_geom), sizeof(dn_consts), offsetof(dn_mask, value), offsetof(dn_geom, hx),'
-                   ' offsetof(dn_geom, mean_count), offsetof(dn_consts, reduction)); return 0;}\n')
+                   ' offsetof(dn_geom, mean_count), offsetof(dn_consts, reduction), sizeof(dn_slab_link),'
+                   ' offsetof(dn_slab_link, put_plane), offsetof(dn_slab_link, max_spins), offsetof(dn_slab_link, world));'
+                   ' return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
     want = [C.sizeof(L.dn_field), C.sizeof(L.dn_mask), C.sizeof(L.dn_geom), C.sizeof(L.dn_consts),
             L.dn_mask.value.offset, L.dn_geom.hx.offset, L.dn_geom.mean_count.offset,
-            L.dn_consts.reduction.offset]
+            L.dn_consts.reduction.offset, C.sizeof(L.dn_slab_link), L.dn_slab_link.put_plane.offset,
+            L.dn_slab_link.max_spins.offset, L.dn_slab_link.world.offset]
     assert got == want
 
 

@@ -264,6 +264,62 @@ def test_z_slab_ownership_matches_whole_domain():
     assert rel_l2(torch.cat(parts, 1), grad) < 1e-6
 
 
+def test_linked_slab_launch_on_one_gpu():
+    """dn_fem_energy_3d_linked_f32 (halo exchange + loss push inside the FEM launch) with the
+    neighbours EMULATED by pre-filled staging planes and released flags, so nothing waits: the halo
+    planes are read from staging (the slab's own halo planes hold junk), the boundary planes land
+    in the 'neighbours'' buffers with the launch number in their flags, the loss partial lands in
+    the slot table, and loss / owned gradient equal the plain launch on the slab with halos in place."""
+    import ctypes as C
+    from diffnet_b200 import _lib as L, ops
+    N, lo, hi = 32, 9, 23                      # stored planes [lo, hi): owned [lo+1, hi-1)
+    fem = DiffNet3DFEM(None, domain_size=N)
+    u, nu, f, src, sink = (t.to(DEV)[0, 0] for t in make_inputs(1, N, N, N, seed=91))
+    nl, o0, o1 = hi - lo, 1, hi - lo - 1
+    geom = ops.Geometry(3, N, N, nl, fem.hx, fem.hy, fem.hz, 2)
+    count = float((N - 1) ** 3)
+    sl = lambda t: t[lo:hi].contiguous()       # noqa: E731
+    kw = dict(nu=sl(nu), f=sl(f), dirichlet=[(sl(src), 0.0)], c_k=0.5)
+    lref, gref, _ = ops.energy_raw(geom, sl(u), z_own=(o0, o1), mean_count=count, **kw)
+    ul = u[lo:hi].clone()                      # (a slice along z is already contiguous: sl() would alias u)
+    ul[0] = 777.0
+    ul[-1] = -777.0
+    staging = torch.stack([u[lo], u[hi - 1]]).contiguous()
+    flags = torch.zeros(64, dtype=torch.int32, device=DEV)          # [0,1] halo flags, [32,33] "remote" flags
+    remote = torch.full((2, N * N), float("nan"), device=DEV)
+    area = torch.zeros(4, dtype=torch.float64, device=DEV)          # double[1] slot + int32[1] flag (+ slack)
+    table = torch.tensor([area.data_ptr()], dtype=torch.int64, device=DEV)
+    ctrl = torch.zeros(4, dtype=torch.int32, device=DEV)            # step, status, tickets[2]
+    lk = L.dn_slab_link()
+    for sd, plane in ((0, o0), (1, o1 - 1)):
+        lk.halo_plane[sd] = staging[sd].data_ptr()
+        lk.halo_flag[sd] = flags.data_ptr() + 4 * sd
+        lk.put_dst[sd] = remote[sd].data_ptr()
+        lk.put_flag[sd] = flags.data_ptr() + 4 * (32 + sd)
+        lk.put_plane[sd] = plane
+    lk.loss_slots = table.data_ptr()
+    lk.step, lk.status, lk.tickets = ctrl.data_ptr(), ctrl.data_ptr() + 4, ctrl.data_ptr() + 8
+    lk.max_spins, lk.rank, lk.world = 1 << 16, 0, 1
+    call = ops.PreparedEnergy(geom, ul, z_own=(o0, o1), mean_count=count, link=lk, **kw)
+    for step in (1, 2, 3):
+        flags[:2] = step                        # the neighbours have "released" this step
+        remote.fill_(float("nan"))
+        loss, grad = call()
+        torch.cuda.synchronize()
+        assert int(ctrl[0]) == step and int(ctrl[1]) == 0
+        assert torch.equal(grad.reshape(nl, N, N)[o0:o1], gref.reshape(nl, N, N)[o0:o1])
+        assert torch.equal(loss, lref)
+        assert torch.equal(remote[0], ul[o0].reshape(-1)) and torch.equal(remote[1], ul[o1 - 1].reshape(-1))
+        assert flags[32:34].tolist() == [step, step]
+        assert float(area[0]) == pytest.approx(float(lref), rel=1e-7)
+        assert int(area[1:2].view(torch.int32)[0]) == step
+    # a flag that never arrives: bounded wait, status word set, no hang
+    flags[:2] = 0
+    call()
+    torch.cuda.synchronize()
+    assert int(ctrl[1]) == 1
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node")
 def test_peer_memory_halo_transport_two_gpus():
     """tools/slab_peer_check.py under torchrun on 2 GPUs: the NVLink peer-memory transport
@@ -278,6 +334,7 @@ def test_peer_memory_halo_transport_two_gpus():
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "'loss_equal': True" in r.stdout and "'grad_equal': True" in r.stdout and "'u_equal': True" in r.stdout
+    assert "'linked_grad_equal': True" in r.stdout and "'linked_graph_grad_equal': True" in r.stdout
 
 
 def test_randomised_parity_sweep():

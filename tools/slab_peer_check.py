@@ -64,6 +64,30 @@ for transport in ("nccl", "peer"):
         res["graph_vs_eager_loss_rel"] = abs(float(lg) - float(le)) / abs(float(le))
         res["graph_vs_eager_grad_max"] = float((gg - ge)[sp.slab.own_local[0]:sp.slab.own_local[1]].abs().max())
         assert not sp._peer_halo.timed_out(), "device-side wait timed out (graph)"
+# ---- linked (one-launch) steps: same loss (after the on-demand sum) and gradient, bit for bit
+sp = ZSlabPoisson3D(geom, transport="peer")
+sp.set_fields(nu=nu, f=f, dirichlet=[(bc, 0.0)], already_local=True, c_k=0.5)
+uref = outs["peer"][2]                                   # halos refreshed by the put/wait path
+o0, o1 = sp.slab.own_local
+for it in range(3):
+    ul = uref.clone()
+    ul[:o0] = 12345.0; ul[o1:] = -54321.0                # the linked kernel must NOT read the local halo planes
+    lpart, gl = sp.step_linked(ul)
+    ltot = sp.global_loss()
+    torch.cuda.synchronize()
+sp.check()
+res["linked_loss_equal"] = bool(torch.equal(ltot, outs["peer"][0]))
+res["linked_loss_rel"] = abs(float(ltot) - float(outs["peer"][0])) / abs(float(outs["peer"][0]))
+res["linked_grad_equal"] = bool(torch.equal(gl[o0:o1], outs["peer"][1][o0:o1]))
+res["linked_eager_ms"] = timeit(lambda: sp.step_linked(uref))
+rpl = sp.capture(uref, linked=True)
+res["linked_graph_ms"] = timeit(rpl)
+lg2, gg2 = rpl(); lg2, gg2 = rpl()
+ltot2 = sp.global_loss()
+torch.cuda.synchronize()
+sp.check()
+res["linked_graph_loss_equal"] = bool(torch.equal(ltot2, outs["peer"][0]))
+res["linked_graph_grad_equal"] = bool(torch.equal(gg2[o0:o1], outs["peer"][1][o0:o1]))
 ln, gn, un = outs["nccl"]; lp, gp, up = outs["peer"]
 res["loss_equal"] = bool(torch.equal(ln, lp)); res["grad_equal"] = bool(torch.equal(gn, gp)); res["u_equal"] = bool(torch.equal(un, up))
 if rank == 0:
