@@ -325,7 +325,8 @@ constexpr int kXParity = kXHa + kXPre + DN_T3_MAXT + 4;      // floats per parit
 constexpr int kXTrash = kXPre + DN_T3_MAXT + 2;              // slot index (within hb / ha) nobody reads
 __host__ __device__ constexpr int xbuf_bytes() { return 2 * kXParity * 4; }
 
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI, bool ISO>
+// LK: linked z-slab launch (dn_slab_link) -- separate instantiations, so that the plain kernels carry none of it
+template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI, bool ISO, bool LK>
 __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_constant__ P3T p) {
   using F = Fem3T<NM, VF, HAS_NU, HAS_F, NUMASK, MI, ISO>;
   constexpr int NF = F::NF;
@@ -344,7 +345,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   // ---- linked z-slab launch: the first 2 * nput CTAs push this rank's boundary planes of u into the
   // neighbours' staging buffers (plain vectorised stores over NVLink), release the neighbours' flag
   // words (system scope, last CTA of a side through a ticket) and are done
-  const int nputc = 2 * p.lk.nput;
+  const int nputc = LK ? 2 * p.lk.nput : 0;
   int want = 0;
   if (nputc) {
     pdl_wait();
@@ -391,6 +392,11 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   // multiple of 4 nodes at or below the first node of lane 0
   const int xs = (2 * pfirst) & ~3, xoff = 2 * pfirst - xs;
 
+  // Linked launch, chunk that starts at the lower halo plane: march DOWN instead of up, so that the plane
+  // the neighbour sends is needed last and its arrival hides behind the whole chunk.  The element code is
+  // untouched: fed (upper, lower) instead of (lower, upper) it solves the z-mirrored problem, whose energy
+  // and nodal gradients are the same numbers (every operation is sign-symmetric).
+  const bool rev = LK && nputc && p.lk.hflag[0] && izc == 0 && (p.nzc > 1 || !p.lk.hflag[1]);
   // ---- producer: one elected lane of warp 0 issues one tensor copy per field per plane
   int issued = 0, ist = 0;
   auto issue_plane = [&]() {         // warp 0 only (warp-uniform)
@@ -398,10 +404,10 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
       uint64_t* bar = full + ist;
       float* dst = ring + ist * stage_floats;
       mbar_arrive_expect_tx(bar, (uint32_t)(NF * BX * p.BY * 4));
-      const int zpl = zf + issued;
+      const int zpl = rev ? zl - issued : zf + issued;
       // linked z-slab launch: the halo planes of u come from the staging buffers the neighbours fill;
       // only the CTAs whose chunk touches them wait (bounded) for this step's flag
-      const int hs = nputc ? ((zpl == 0 && p.lk.hflag[0]) ? 0 : ((zpl == p.nz - 1 && p.lk.hflag[1]) ? 1 : -1)) : -1;
+      const int hs = (LK && nputc) ? ((zpl == 0 && p.lk.hflag[0]) ? 0 : ((zpl == p.nz - 1 && p.lk.hflag[1]) ? 1 : -1)) : -1;
       if (hs >= 0) {
         long long spins = 0;
         int seen;
@@ -451,8 +457,8 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   const bool own_a = rvalid && (lx >= p.hl) && (er >= ty0);   // node row a is stored by this thread; element row owned
   const float2 vw = f2(phantom ? 0.f : 1.f, (has_right && !phantom) ? 1.f : 0.f);
   const K3& k = p.k3;
-  float* gptr = p.grad ? p.grad + ((((long long)b * p.nz + zf) * p.ny + er) * nx + (lvalid ? x0 : 0)) : nullptr;
-  const long long plane_elems = (long long)p.ny * nx;
+  float* gptr = p.grad ? p.grad + ((((long long)b * p.nz + (rev ? zl : zf)) * p.ny + er) * nx + (lvalid ? x0 : 0)) : nullptr;
+  const long long plane_elems = rev ? -(long long)p.ny * nx : (long long)p.ny * nx;   // towards the next plane of the march
   const bool st_a = own_a && (gptr != nullptr);
   const float ew = (own_a && !phantom) ? k.kscale : 0.f;   // energy weight of this thread's element row
   const int elo = max(z0, p.zloss_lo), ecnt = p.zloss_hi - elo;
@@ -531,7 +537,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     gptr += plane_elems;
   };
 
-  // ---- first two planes (npl >= 2): nothing below the first
+  // ---- first two planes of the march (npl >= 2): nothing before the first
   mbar_wait_u32(cbar, phase);
   F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, PA.u, PA.n, PA.f, PA.keep);
   arrive();
@@ -539,11 +545,17 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   wait_all();
   refill();                  // the stage of the first plane
 
-  // element layer s between plane s (L) and plane s+1 (U), both in registers
+  // element layer between the plane in L and the next plane of the march in U (both in registers).
+  // `s` counts the layers from zf upwards; going up it IS the layer's index in the mesh (= its lower
+  // plane) and the plane gathered and stored afterwards; going down (rev) those are mirrored in the chunk.
   auto layer = [&](Plane& L, Plane& U, const int s, const uint32_t po) {
+    int sl = s, pl = s;
+    if constexpr (LK) {
+      if (rev) { sl = zl - 1 - (s - zf); pl = zl - (s - zf); }
+    }
     Face gLo, gUp;
     const float2 E = F::elem_pair(k, L.u, U.u, L.n, U.n, L.f, U.f, vw, gLo, gUp);
-    const float wl = (!resid && (unsigned)(s - elo) < (unsigned)ecnt) ? ew : 0.f;
+    const float wl = (!resid && (unsigned)(sl - elo) < (unsigned)ecnt) ? ew : 0.f;
     e32 = fmaf(wl, E.x + E.y, e32);
     const RowG lo = face_to_rows(gLo);
     RowG done;
@@ -551,12 +563,13 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     done.sb = add2(up.sb, lo.sb); done.db = add2(up.db, lo.db);
     up = face_to_rows(gUp);
     const float2 Na01 = publish(done, po);
-    arrive();              // this warp has read the stage of plane s+1 and published its sums of plane s
+    arrive();              // this warp has read the stage of the U plane and published its sums of the L plane
     const float2 keepL = L.keep;
-    if (s + 2 <= zl) load_next(L);      // plane s+2 replaces plane s in registers
-    wait_all();            // every warp has arrived: partial sums of plane s visible, stage of plane s+1 free
+    if (s + 2 <= zl) load_next(L);      // the plane after U replaces L in registers
+    wait_all();            // every warp has arrived: partial sums visible, the oldest stage is free
     refill();
-    finalize(Na01, keepL, po, s >= z0);
+    if constexpr (LK) finalize(Na01, keepL, po, pl >= z0 && pl < z1);
+    else finalize(Na01, keepL, po, s >= z0);
   };
   int s = zf;
   for (; s + 1 < zl; s += 2) {
@@ -568,8 +581,9 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   const bool odd = s < zl;
   if (odd) layer(PA, PB, s, 0u);
 
-  // ---- top node plane of the domain: no element layer above it
-  if (z1 == p.nz) {
+  // ---- the last plane of the march when this chunk owns it (top plane of the domain going up, bottom
+  // plane going down): no element layer beyond it
+  if (rev ? (z0 == 0) : (z1 == p.nz)) {
     const uint32_t po = odd ? kPAR : 0u;
     const float2 Na01 = publish(up, po);
     arrive();
@@ -591,32 +605,32 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
 // ---- dispatch (fem3d_tma_dispatch.cu) --------------------------------------------------------
 typedef cudaError_t (*launch3t_fn)(const P3T&, dim3, dim3, size_t, cudaStream_t);
 typedef int (*occ3t_fn)(int, size_t);
-launch3t_fn get_launch3t(int MK, int NU, int F, int NUMASK);
-occ3t_fn get_occ3t(int MK, int NU, int F, int NUMASK);
+launch3t_fn get_launch3t(int MK, int NU, int F, int NUMASK, int LK);
+occ3t_fn get_occ3t(int MK, int NU, int F, int NUMASK, int LK);
 
-template <int MK, int NUK, bool HAS_F, bool NUMASK>
+template <int MK, int NUK, bool HAS_F, bool NUMASK, bool LK>
 struct Kern3T {
   // MK 0..3 / 4 / 5..7 as in fem2d_tma.cuh (5..7: mask_input = 0)
   static constexpr int NM = (MK == 4) ? 1 : (MK >= 5 ? MK - 4 : MK);
-  static auto get() { return k_fem3d_tma<NM, (MK == 4), (NUK != 0), HAS_F, NUMASK, (MK < 5), (NUK == 2)>; }
+  static auto get() { return k_fem3d_tma<NM, (MK == 4), (NUK != 0), HAS_F, NUMASK, (MK < 5), (NUK == 2), LK>; }
 };
 
-template <int MK, int NUK, bool HAS_F, bool NUMASK>
+template <int MK, int NUK, bool HAS_F, bool NUMASK, bool LK>
 cudaError_t prep3t() {
   static bool done[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  e = cudaFuncSetAttribute(Kern3T<MK, NUK, HAS_F, NUMASK>::get(),
+  e = cudaFuncSetAttribute(Kern3T<MK, NUK, HAS_F, NUMASK, LK>::get(),
                            cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
   if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
   return e;
 }
 
-template <int MK, int NUK, bool HAS_F, bool NUMASK>
+template <int MK, int NUK, bool HAS_F, bool NUMASK, bool LK>
 cudaError_t launch3t(const P3T& p, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
-  cudaError_t e = prep3t<MK, NUK, HAS_F, NUMASK>();
+  cudaError_t e = prep3t<MK, NUK, HAS_F, NUMASK, LK>();
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -625,14 +639,14 @@ cudaError_t launch3t(const P3T& p, dim3 grid, dim3 block, size_t smem, cudaStrea
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   if (pdl_enabled()) { cfg.attrs = at; cfg.numAttrs = 1; }
-  return cudaLaunchKernelEx(&cfg, Kern3T<MK, NUK, HAS_F, NUMASK>::get(), p);
+  return cudaLaunchKernelEx(&cfg, Kern3T<MK, NUK, HAS_F, NUMASK, LK>::get(), p);
 }
 
-template <int MK, int NUK, bool HAS_F, bool NUMASK>
+template <int MK, int NUK, bool HAS_F, bool NUMASK, bool LK>
 int occ3t(int threads, size_t smem) {
-  if (prep3t<MK, NUK, HAS_F, NUMASK>() != cudaSuccess) return 0;
+  if (prep3t<MK, NUK, HAS_F, NUMASK, LK>() != cudaSuccess) return 0;
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern3T<MK, NUK, HAS_F, NUMASK>::get(), threads,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern3T<MK, NUK, HAS_F, NUMASK, LK>::get(), threads,
                                                     smem) != cudaSuccess)
     return 0;
   return n;

@@ -9,25 +9,25 @@
 #include "fem3d_tma_combos.h"
 
 namespace dn {
-#define DN_EXT(MK, NU, F, NMK)                                                                        \
-  extern template cudaError_t launch3t<MK, NU, F, NMK>(const P3T&, dim3, dim3, size_t, cudaStream_t); \
-  extern template int occ3t<MK, NU, F, NMK>(int, size_t);
+#define DN_EXT(MK, NU, F, NMK, LK)                                                                        \
+  extern template cudaError_t launch3t<MK, NU, F, NMK, LK>(const P3T&, dim3, dim3, size_t, cudaStream_t); \
+  extern template int occ3t<MK, NU, F, NMK, LK>(int, size_t);
 DN3T_ALL(DN_EXT)
 #undef DN_EXT
 
-launch3t_fn get_launch3t(int MK, int NU, int F, int NUMASK) {
-#define DN_CASE(MK_, NU_, F_, NMK_)                                                \
-  if (MK == MK_ && NU == (int)NU_ && F == (int)F_ && NUMASK == (int)NMK_)          \
-    return &launch3t<MK_, NU_, F_, NMK_>;
+launch3t_fn get_launch3t(int MK, int NU, int F, int NUMASK, int LK) {
+#define DN_CASE(MK_, NU_, F_, NMK_, LK_)                                                          \
+  if (MK == MK_ && NU == (int)NU_ && F == (int)F_ && NUMASK == (int)NMK_ && LK == (int)LK_)       \
+    return &launch3t<MK_, NU_, F_, NMK_, LK_>;
   DN3T_ALL(DN_CASE)
 #undef DN_CASE
   return nullptr;
 }
 
-occ3t_fn get_occ3t(int MK, int NU, int F, int NUMASK) {
-#define DN_CASE(MK_, NU_, F_, NMK_)                                                \
-  if (MK == MK_ && NU == (int)NU_ && F == (int)F_ && NUMASK == (int)NMK_)          \
-    return &occ3t<MK_, NU_, F_, NMK_>;
+occ3t_fn get_occ3t(int MK, int NU, int F, int NUMASK, int LK) {
+#define DN_CASE(MK_, NU_, F_, NMK_, LK_)                                                          \
+  if (MK == MK_ && NU == (int)NU_ && F == (int)F_ && NUMASK == (int)NMK_ && LK == (int)LK_)       \
+    return &occ3t<MK_, NU_, F_, NMK_, LK_>;
   DN3T_ALL(DN_CASE)
 #undef DN_CASE
   return nullptr;
@@ -93,7 +93,7 @@ static size_t smem_3t(int S, int nf, int fstride) {
 //   SM time ~ ceil(grid / SMs) * threads * (ZC + 1)   [thread-layers executed by the busiest SM]
 // with a penalty when fewer than 12 warps per SM are resident and a mild preference for one wave.
 // `occ` may be null (workspace sizing): then the register bound is assumed.
-static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_variant) {
+static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_variant, long long min_grid = 0) {
   Plan3T best;
   memset(&best, 0, sizeof(best));
   if (g->nx % 4 != 0 || g->nx < 8) return best;
@@ -153,6 +153,7 @@ static Plan3T plan3t(const dn_geom* g, int nf, int sms, occ3t_fn occ, int maxt_v
         const int nzc = (g->nz + ZC - 1) / ZC;
         if (zc_forced <= 0 && nzc != nzc_try) continue;
         const long long grid = tiles * nzc;
+        if (grid < min_grid && nzc_try < nzc_max) continue;          // linked launches want >= 2 waves (see the kernel)
         const long long per_sm = (grid + sms - 1) / sms;             // CTAs the busiest SM runs
         const long long resident = per_sm < cps ? per_sm : cps;
         const double waves = (double)((per_sm + cps - 1) / cps);
@@ -212,8 +213,8 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
     else if (MK >= 1 && MK <= 3 && !F && !NMK) MKx = MK + 4;
     else return DN_OK;
   }
-  launch3t_fn fn = get_launch3t(MKx, NU, F, NMK);
-  occ3t_fn occ = get_occ3t(MKx, NU, F, NMK);
+  launch3t_fn fn = get_launch3t(MKx, NU, F, NMK, link ? 1 : 0);
+  occ3t_fn occ = get_occ3t(MKx, NU, F, NMK, link ? 1 : 0);
   if (!fn || !occ || !get_encode()) return DN_OK;
   Field fl[DN_T2_MAXF];
   P3T p;
@@ -225,7 +226,8 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   if (NMK) fl[nf++] = numask;
   for (int i = 0; i < nmasks; ++i) { fl[nf++] = mk[i].m; p.mval[i] = mk[i].v; }
   if (MK == 4) fl[nf++] = mk[0].vf;
-  Plan3T pl = plan3t(g, nf, sms, occ, DN_T3_MAXT_OF(NU));
+  const long long min_grid = (link && link->halo_plane[0] && env_i3("DN_SLAB_WAVES", 0)) ? (long long)(1.9 * sms) : 0;
+  Plan3T pl = plan3t(g, nf, sms, occ, DN_T3_MAXT_OF(NU), min_grid);
   if (!pl.ok) { cudaGetLastError(); return DN_OK; }
   if (pl.grid > 0x7fffffffLL) return DN_OK;
   int nput = 0;

@@ -3,9 +3,9 @@
 #include "fem3d_tma.cuh"
 #include "fem3d_tma_combos.h"
 namespace dn {
-#define DN_INST(MK, NU, F, NMK)                                                                 \
-  template cudaError_t launch3t<MK, NU, F, NMK>(const P3T&, dim3, dim3, size_t, cudaStream_t);  \
-  template int occ3t<MK, NU, F, NMK>(int, size_t);
+#define DN_INST(MK, NU, F, NMK, LK)                                                                 \
+  template cudaError_t launch3t<MK, NU, F, NMK, LK>(const P3T&, dim3, dim3, size_t, cudaStream_t);  \
+  template int occ3t<MK, NU, F, NMK, LK>(int, size_t);
 #if DN_MK >= 5
 DN3T_COMBOS_OP(DN_INST, DN_MK)
 #else
