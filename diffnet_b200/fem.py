@@ -104,6 +104,55 @@ class DiffNetFEM(PDE):
             setattr(self, n, lists[n])          # registered: appear in state_dict like the reference
         for n in vnames:
             setattr(self, n, values[n])
+        # The reference also registers the second-derivative stencils (identically zero for Q1) and, in
+        # 2-D, the 1-D surface stencils (DiffNetFEM.py:187-195,244-269, 391-403): they are part of its
+        # state_dict, so a checkpoint written by the reference loads here with strict=True and vice versa.
+        # d2N_{x,y,z} are identically zero for Q1; the mixed ones are not.  In 3-D the reference writes
+        # them with TRANSPOSED local indices [ibf, jbf, kbf] (DiffNetFEM.py:430-435): kept,
+        # the point is an identical state_dict.
+        D = [-0.5, 0.5]
+        gx = [float(x) for x in self.gpx_1d]
+        bf = lambda x, i: float(self.bf_1d(x)[i])       # noqa: E731
+        mixed = {}
+        zero = lambda: [torch.zeros((2,) * nsd) for _ in range(self.ngp_total)]   # noqa: E731
+        if nsd == 2:
+            second = ["d2N_x_gp", "d2N_y_gp", "d2N_xy_gp"]
+            mixed["d2N_xy_gp"] = zero()
+            for G in range(self.ngp_total):
+                for jb in range(2):
+                    for ib in range(2):
+                        mixed["d2N_xy_gp"][G][jb, ib] = D[ib] * D[jb] * (2 / self.hx) * (2 / self.hy)
+        else:
+            second = ["d2N_x_gp", "d2N_y_gp", "d2N_z_gp", "d2N_xy_gp", "d2N_yz_gp", "d2N_zx_gp"]
+            for n in ("d2N_xy_gp", "d2N_yz_gp", "d2N_zx_gp"):
+                mixed[n] = zero()
+            for G, (kg, jg, ig) in enumerate(np.ndindex(ng, ng, ng)):
+                for kb in range(2):
+                    for jb in range(2):
+                        for ib in range(2):
+                            mixed["d2N_xy_gp"][G][ib, jb, kb] = D[ib] * D[jb] * bf(gx[kg], kb) * (2 / self.hx) * (2 / self.hy)
+                            mixed["d2N_yz_gp"][G][ib, jb, kb] = bf(gx[ig], ib) * D[jb] * D[kb] * (2 / self.hy) * (2 / self.hz)
+                            mixed["d2N_zx_gp"][G][ib, jb, kb] = D[ib] * bf(gx[jg], jb) * D[kb] * (2 / self.hz) * (2 / self.hx)
+        for n in second:
+            tabs = mixed.get(n) or zero()
+            setattr(self, n, nn.ParameterList([nn.Parameter(t[None, None].clone(), requires_grad=False) for t in tabs]))
+        if nsd == 2:
+            self.gpw_surf = torch.tensor([float(w) for w in self.gpw_1d], dtype=torch.float32)
+            surf = {"N_gp_surf": [], "dN_x_gp_surf": [], "dN_y_gp_surf": []}
+            self.Nvalues_surf = torch.ones((1, self.nbf_1d, ng, 1))
+            self.dN_x_values_surf = torch.ones((1, self.nbf_1d, ng, 1))
+            self.dN_y_values_surf = torch.ones((1, self.nbf_1d, ng, 1))
+            for igp in range(ng):
+                row = {"N_gp_surf": torch.tensor(val[igp], dtype=torch.float32),
+                       "dN_x_gp_surf": torch.tensor(der[igp] * (2.0 / self.hx), dtype=torch.float32),
+                       "dN_y_gp_surf": torch.tensor(der[igp] * (2.0 / self.hy), dtype=torch.float32)}
+                self.Nvalues_surf[0, :, igp, 0] = row["N_gp_surf"]
+                self.dN_x_values_surf[0, :, igp, 0] = row["dN_x_gp_surf"]
+                self.dN_y_values_surf[0, :, igp, 0] = row["dN_y_gp_surf"]
+                for k, v in row.items():
+                    surf[k].append(nn.Parameter(v[None, None].clone(), requires_grad=False))
+            for k, v in surf.items():
+                setattr(self, k, nn.ParameterList(v))
 
         x = np.linspace(0, self.domain_lengthX, self.domain_sizeX)
         y = np.linspace(0, self.domain_lengthY, self.domain_sizeY)

@@ -8,8 +8,26 @@ Neither is on the measured FEM hot path; they exist so the train-step benchmark 
 reference's parameter count to all-reduce."""
 from __future__ import annotations
 
+import re
+
 import torch
 from torch import nn
+
+
+def _from_reference_key(k: str) -> str:
+    """``down3.model.0.weight`` / ``up2.model.1.weight`` / ``final.2.bias`` (DiffNet/networks/unets.py:49-66)
+    -> ``enc.2.0.weight`` / ``dec.1.1.weight`` / ``head.2.bias``; other keys unchanged."""
+    m = re.match(r"(.*?)(down|up)(\d+)\.model\.(.*)$", k)
+    if m:
+        return f"{m.group(1)}{'enc' if m.group(2) == 'down' else 'dec'}.{int(m.group(3)) - 1}.{m.group(4)}"
+    return re.sub(r"(^|\.)final\.", r"\1head.", k)
+
+
+def _to_reference_key(k: str) -> str:
+    m = re.match(r"(.*?)(enc|dec)\.(\d+)\.(.*)$", k)
+    if m:
+        return f"{m.group(1)}{'down' if m.group(2) == 'enc' else 'up'}{int(m.group(3)) + 1}.model.{m.group(4)}"
+    return re.sub(r"(^|\.)head\.", r"\1final.", k)
 
 _ENC = ((32, False, 0.0), (64, True, 0.0), (128, True, 0.0), (256, True, 0.5), (256, True, 0.5))
 _DEC = ((256, 256, 0.5), (512, 128, 0.5), (256, 64, 0.0), (128, 32, 0.0))   # (in, out, dropout)
@@ -57,6 +75,19 @@ class UNet(nn.Module):
         pad = nn.ZeroPad2d((1, 0, 1, 0)) if nd == 2 else nn.ConstantPad3d((1, 0, 1, 0, 1, 0), 0.0)
         self.head = nn.Sequential(nn.Upsample(scale_factor=2), pad, conv(64 // scale, out_channels, 4, padding=1),
                                   nn.Sigmoid())
+        # weights saved by the reference's UNet (down1..down5 / up1..up4 / final) load as they are
+        self._register_load_state_dict_pre_hook(self._accept_reference_keys)
+
+    @staticmethod
+    def _accept_reference_keys(state_dict, prefix, *args):
+        for k in [k for k in state_dict if k.startswith(prefix)]:
+            nk = prefix + _from_reference_key(k[len(prefix):])
+            if nk != k:
+                state_dict[nk] = state_dict.pop(k)
+
+    def reference_state_dict(self):
+        """state_dict under the reference's parameter names (for its ``UNet.load_state_dict``)."""
+        return {_to_reference_key(k): v for k, v in self.state_dict().items()}
 
     def forward(self, x):
         skips = []

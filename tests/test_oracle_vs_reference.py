@@ -91,3 +91,28 @@ def test_3d_losses_bit_exact(ref):
     lr, lo = L.body_ibn3d(r, ur, src, sink, f), L.body_ibn3d(o, uo, src, sink, f)
     lr.backward(); lo.backward()
     assert torch.equal(lr, lo) and torch.equal(ur.grad, uo.grad)
+
+
+def test_reference_checkpoints_load_strictly():
+    """A state_dict written by the reference's DiffNet2DFEM / DiffNet3DFEM / UNet loads into the
+    diffnet_b200 classes with strict=True (same keys, same shapes, same table values), and back."""
+    import importlib
+    from diffnet_b200 import DiffNet2DFEM, DiffNet3DFEM
+    from diffnet_b200.networks import UNet
+    ref = load_reference()
+    for ours, theirs in ((DiffNet2DFEM(None, domain_size=16), ref.DiffNet2DFEM(None, domain_size=16)),
+                         (DiffNet3DFEM(None, domain_size=8), ref.DiffNet3DFEM(None, domain_size=8, nsd=3))):
+        sd = theirs.state_dict()
+        assert set(sd) == set(ours.state_dict())
+        for k, v in ours.state_dict().items():
+            assert torch.equal(v, sd[k]), k
+        ours.load_state_dict(sd, strict=True)
+        theirs.load_state_dict(ours.state_dict(), strict=True)
+    unets = importlib.import_module("DiffNet.networks.unets")
+    torch.manual_seed(0)
+    rnet, net = unets.UNet(3, 1).eval(), UNet(3, 1).eval()
+    net.load_state_dict(rnet.state_dict(), strict=True)
+    x = torch.rand(2, 3, 64, 64)
+    with torch.no_grad():
+        assert torch.equal(net(x), rnet(x))
+    rnet.load_state_dict(net.reference_state_dict(), strict=True)
