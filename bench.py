@@ -228,6 +228,75 @@ def time_workload(name, dev, seed, K, W, reps, world=1, barrier=None, use_graph=
     return {"ms_step": ms_step, "mode": mode, "sets": sets, "fem": fem, "nsets": nsets}
 
 
+def time_ops(name, dev, K, reps=3):
+    """The path's other operators at a BASELINE shape: the residual-minimisation form
+    (forward operator pass + the backward operator pass, `resmin*`) and the un-fused
+    gauss_pt_evaluation (`gp_eval*`, write-bound), graph-replayed like the headline.
+    Returns {ms_per_step, bytes (algorithmic, per step), value GDOF/s}."""
+    import torch
+    from diffnet_b200 import ops
+    kind, base = name.split(":")
+    nsd, size, B, _, _ = WORKLOADS[base]
+    fem = make_fem(base)
+    dof = B * size ** nsd
+    nsets = min(16, max(2, int(-(-400e6 // (dof * 24)))))
+    sets = [make_inputs(base, dev, seed=777 + i) for i in range(nsets)]
+    if kind == "resmin":
+        jac = (0.5 * fem.h) ** nsd
+
+        def step(i):
+            s = sets[i % nsets]
+            kw = {k: v for k, v in call_kwargs(s).items() if k in ("nu", "f", "dirichlet")}
+            _, R = ops.residual_raw(fem.geometry, s["u"], jac=jac, apply_masks_to_input=True, **kw)
+            kwb = {k: v for k, v in kw.items() if k in ("nu", "dirichlet")}
+            return ops.residual_raw(fem.geometry, R, jac=jac, apply_masks_to_input=False, **kwb)
+        nin = 5 if nsd == 2 else len(sets[0]["_fields"])                # 2-D: u, nu, bc1, bc2, f
+        nbytes = dof * 4 * ((nin + 1) + (nin - 1 + 1))                   # pass 1: fields -> R; pass 2: R, nu, masks -> K R
+    else:
+        ngp = 2 ** nsd
+        nel = B * (size - 1) ** nsd
+
+        def step(i):
+            return ops._gp_raw(fem.geometry, sets[i % nsets]["u"], 0)
+        nbytes = dof * 4 + nel * ngp * 4
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(0)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for i in range(K):
+            step(i)
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / K)
+    ms = sorted(ts)[len(ts) // 2]
+    peak, _ = measured_peak_gbs()
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"value": dof / (ms * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": ms, "algorithmic_bytes_per_step": nbytes,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak},
+            "launches_per_step": 2 if kind == "resmin" else 1,
+            "desc": ("residual form: operator pass + backward operator pass, " if kind == "resmin"
+                     else "gauss_pt_evaluation (un-fused, N table), ") + WORKLOADS[base][4]}
+
+
+OPS_POINTS = ["resmin:poisson2d_param_256_b64", "resmin:poisson3d_param_64_b16",
+              "gp_eval:poisson2d_param_256_b64", "gp_eval:poisson3d_param_64_b16"]
+
+
 def point_of(name, res, peak, clock_mhz=None):
     """One entry of `points`: a BASELINE config (or named roofline point) measured like the headline."""
     nsd, size, B, bpd, desc = WORKLOADS[name]
@@ -469,6 +538,12 @@ def run_ours(args):
                 points[pn] = point_of(pn, r, peak0)
                 del r
             except Exception as e:   # noqa: BLE001  (the headline must still be printed)
+                points[pn] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+        for pn in OPS_POINTS:
+            try:
+                points[pn] = time_ops(pn, dev, 20)
+            except Exception as e:   # noqa: BLE001
                 points[pn] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
     clocks = sampler.stop() if rank == 0 else None

@@ -11,7 +11,9 @@ for k, v in (d.get("points") or {}).items():
     if "error" in v:
         print(f"  {k:26s} ERROR {v['error']}")
     else:
-        print(f"  {k:26s} {v['value']:7.1f} GDOF/s  {v['ms_per_step'] * 1e3:8.2f} us  hbm {v['roofline']['frac']:.3f}  fp32 {v['secondary']['frac']:.3f}  {v['launch']}")
+        sec = v.get("secondary", {}).get("frac")
+        print(f"  {k:34s} {v['value']:7.1f} GDOF/s  {v['ms_per_step'] * 1e3:8.2f} us  hbm {v['roofline']['frac']:.3f}"
+              + (f"  fp32 {sec:.3f}" if sec is not None else "") + f"  {v.get('launch', '')}")
 if d.get("slab"):
     s = d["slab"]
     print("  slab:", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in s.items() if k not in ("desc", "l2", "roofline_per_gpu")})

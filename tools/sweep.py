@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""tools/sweep3d.py [workload ...] -- time the fused 3-D launch under a list of env-knob settings in ONE
+"""tools/sweep.py [workload ...] -- time the fused 3-D launch under a list of env-knob settings in ONE
 process (the planners read the environment per call), and cross-check every setting against the
 first one (loss rel. difference, gradient max-norm difference).
 
-    python tools/sweep3d.py --cfg "DN_T3_THREADS=256" --cfg "DN_T3_THREADS=128 DN_T3_LX=16" poisson3d_256_b1
+    python tools/sweep.py --cfg "DN_T3_THREADS=256" --cfg "DN_T3_THREADS=128 DN_T3_LX=16" poisson3d_256_b1
 
 CUDA events around N eager launches through PreparedEnergy (about 5 us of host time per call),
 input sets rotated so that every launch streams from HBM.  A probe tool, not the bench.
@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--cfg", action="append", default=[])
     ap.add_argument("--n", type=int, default=40)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--graph", action="store_true", help="replay the N launches from one CUDA graph (short kernels)")
     a = ap.parse_args()
     cfgs = [""] + a.cfg
     dev = torch.device("cuda", 0)
@@ -58,11 +59,28 @@ def main():
                 dg = float((g0 - ref[1]).abs().max() / ref[1].abs().max())
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 best = 1e9
+                graph = None
+                if a.graph:                      # the knobs are read at capture time: one graph per setting
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        for p in preps:
+                            p()
+                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
+                        for i in range(a.n):
+                            preps[i % nsets]()
+                    graph.replay()
                 for rep in range(3):
                     torch.cuda.synchronize()
                     e0.record()
-                    for i in range(a.n):
-                        preps[i % nsets]()
+                    if graph is not None:
+                        graph.replay()
+                    else:
+                        for i in range(a.n):
+                            preps[i % nsets]()
                     e1.record()
                     torch.cuda.synchronize()
                     best = min(best, e0.elapsed_time(e1) / a.n)
