@@ -32,6 +32,9 @@
 namespace dn {
 
 #define DN_T3_MAXT 640      // largest CTA of any variant
+#ifndef DN_T3_ORDER
+#define DN_T3_ORDER 0
+#endif
 // Register budgets (__maxnreg__; one CTA per SM).  Registers are granted per warp in units of 1024
 // (measured: 112 registers/thread admit no more warps than 128), so the useful budgets are 96 and
 // 128: nu == 1 variants fit 96 without spills -> 640-thread CTAs (20 warps/SM, +4 % measured);
@@ -224,22 +227,46 @@ struct Fem3T {
     }
   }
 
+  // z-stage of one pair of hexahedra: the 8 modes of u (and of nu, f) from the face modes of the lower (L*)
+  // and upper (U*) faces; modes m = 4*zbit + 2*ybit + xbit.  After it the lower faces are dead.
+  struct Modes {
+    float2 u0, u1, u2, u3, u4, u5, u6, u7;
+    float2 C0, C1, C2, C3, C4, C5, C6;
+    float2 F0, F1, F2, F3, F4, F5, F6, F7;
+  };
+  static __device__ __forceinline__ void zstage(const Face& Lu, const Face& Uu, const Face& Ln, const Face& Un,
+                                                const Face& Lf, const Face& Uf, Modes& M) {
+    if constexpr (HAS_F) M.u0 = add2(Lu.m0, Uu.m0);
+    M.u1 = add2(Lu.m1, Uu.m1); M.u2 = add2(Lu.m2, Uu.m2); M.u3 = add2(Lu.m3, Uu.m3);
+    M.u4 = sub2(Uu.m0, Lu.m0); M.u5 = sub2(Uu.m1, Lu.m1); M.u6 = sub2(Uu.m2, Lu.m2); M.u7 = sub2(Uu.m3, Lu.m3);
+    if constexpr (HAS_NU) {
+      M.C0 = add2(Ln.m0, Un.m0); M.C1 = add2(Ln.m1, Un.m1); M.C2 = add2(Ln.m2, Un.m2); M.C3 = add2(Ln.m3, Un.m3);
+      M.C4 = sub2(Un.m0, Ln.m0); M.C5 = sub2(Un.m1, Ln.m1); M.C6 = sub2(Un.m2, Ln.m2);
+    }
+    if constexpr (HAS_F) {
+      M.F0 = add2(Lf.m0, Uf.m0); M.F1 = add2(Lf.m1, Uf.m1); M.F2 = add2(Lf.m2, Uf.m2); M.F3 = add2(Lf.m3, Uf.m3);
+      M.F4 = sub2(Uf.m0, Lf.m0); M.F5 = sub2(Uf.m1, Lf.m1); M.F6 = sub2(Uf.m2, Lf.m2); M.F7 = sub2(Uf.m3, Lf.m3);
+    }
+  }
+
   // One pair of hexahedra between the lower faces L* and the upper faces U*.  Returns the energy
   // pair; gLo / gUp = gradient w.r.t. the face modes of u on the lower / upper face.
   static __device__ __forceinline__ float2 elem_pair(const K3& k, const Face& Lu, const Face& Uu,
                                                      const Face& Ln, const Face& Un, const Face& Lf,
                                                      const Face& Uf, float2 vw, Face& gLo, Face& gUp) {
-    // z-stage: modes m = 4*zbit + 2*ybit + xbit
-    const float2 u1 = add2(Lu.m1, Uu.m1), u2 = add2(Lu.m2, Uu.m2), u3 = add2(Lu.m3, Uu.m3);
-    const float2 u4 = sub2(Uu.m0, Lu.m0), u5 = sub2(Uu.m1, Lu.m1), u6 = sub2(Uu.m2, Lu.m2),
-                 u7 = sub2(Uu.m3, Lu.m3);
+    Modes M;
+    zstage(Lu, Uu, Ln, Un, Lf, Uf, M);
+    return elem_modes(k, M, vw, gLo, gUp);
+  }
+
+  // The element in modal space (everything after the z-stage).
+  static __device__ __forceinline__ float2 elem_modes(const K3& k, const Modes& M, float2 vw, Face& gLo, Face& gUp) {
+    const float2 u1 = M.u1, u2 = M.u2, u3 = M.u3, u4 = M.u4, u5 = M.u5, u6 = M.u6, u7 = M.u7;
     const float2 Q3 = mul2(k.t, u3), Q5 = mul2(k.t, u5), Q6 = mul2(k.t, u6), Q7 = mul2(k.t, u7),
                  Q77 = mul2(k.tt, u7);
     float2 qx0, qx1, qx2, qx3, qy0, qy1, qy2, qy3, qz0, qz1, qz2, qz3;
     if constexpr (HAS_NU) {
-      const float2 C0 = add2(Ln.m0, Un.m0), C1 = add2(Ln.m1, Un.m1), C2 = add2(Ln.m2, Un.m2),
-                   C3 = add2(Ln.m3, Un.m3);
-      const float2 C4 = sub2(Un.m0, Ln.m0), C5 = sub2(Un.m1, Ln.m1), C6 = sub2(Un.m2, Ln.m2);
+      const float2 C0 = M.C0, C1 = M.C1, C2 = M.C2, C3 = M.C3, C4 = M.C4, C5 = M.C5, C6 = M.C6;
       float2 dx0, dx1, dx2, dx3, dy0, dy1, dy2, dy3, dz0, dz1, dz2, dz3;
       if constexpr (ISO) {   // k is applied per node / per thread (K3::kscale): 6 products instead of 12
         const float2 T1 = mul2(k.t, C1), T2 = mul2(k.t, C2), T4 = mul2(k.t, C4);
@@ -269,14 +296,12 @@ struct Fem3T {
                  q6 = add2(qy2, qz2), q7 = add2(qx3, add2(qy3, qz3));
     float2 E, g0, g1, g2, g3, g4, g5, g6, g7;
     if constexpr (HAS_F) {
-      const float2 u0 = add2(Lu.m0, Uu.m0);
+      const float2 u0 = M.u0;
       // t_m = q_m + nb_m with nb_m = -kf t^order(m) f_m, fused: one FFMA2 per mode
-      const float2 nb0 = mul2(k.nkf, add2(Lf.m0, Uf.m0));
-      const float2 t1 = fma2(k.nkft, add2(Lf.m1, Uf.m1), q1), t2 = fma2(k.nkft, add2(Lf.m2, Uf.m2), q2),
-                   t4 = fma2(k.nkft, sub2(Uf.m0, Lf.m0), q4);
-      const float2 t3 = fma2(k.nkftt, add2(Lf.m3, Uf.m3), q3), t5 = fma2(k.nkftt, sub2(Uf.m1, Lf.m1), q5),
-                   t6 = fma2(k.nkftt, sub2(Uf.m2, Lf.m2), q6);
-      const float2 t7 = fma2(k.nkfttt, sub2(Uf.m3, Lf.m3), q7);
+      const float2 nb0 = mul2(k.nkf, M.F0);
+      const float2 t1 = fma2(k.nkft, M.F1, q1), t2 = fma2(k.nkft, M.F2, q2), t4 = fma2(k.nkft, M.F4, q4);
+      const float2 t3 = fma2(k.nkftt, M.F3, q3), t5 = fma2(k.nkftt, M.F5, q5), t6 = fma2(k.nkftt, M.F6, q6);
+      const float2 t7 = fma2(k.nkfttt, M.F7, q7);
       E = fma2(u0, nb0, fma2(u1, t1, fma2(u2, t2, fma2(u3, t3, fma2(u4, t4, fma2(u5, t5, fma2(u6, t6,
                mul2(u7, t7))))))));
       g0 = nb0; g1 = add2(q1, t1); g2 = add2(q2, t2); g3 = add2(q3, t3); g4 = add2(q4, t4);
@@ -541,7 +566,16 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   mbar_wait_u32(cbar, phase);
   F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, PA.u, PA.n, PA.f, PA.keep);
   arrive();
+#if DN_T3_ORDER == 3
+  // Half of the warps of every SM sub-partition ("late" warps) fetch a layer's upper plane at the START of the
+  // layer instead of the end of the previous one: while they run their load/mask phase (LSU, ALU) the other
+  // half runs the modal arithmetic (FMA pipe) and vice versa, instead of all four warps of a scheduler
+  // competing for the same pipe at the same time.
+  const bool late = ((warp >> 2) & 1) != 0;
+  if (!late) load_next(PB);
+#else
   load_next(PB);
+#endif
   wait_all();
   refill();                  // the stage of the first plane
 
@@ -554,7 +588,24 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
       if (rev) { sl = zl - 1 - (s - zf); pl = zl - (s - zf); }
     }
     Face gLo, gUp;
+#if DN_T3_ORDER == 3
+    if (late) load_next(U);
     const float2 E = F::elem_pair(k, L.u, U.u, L.n, U.n, L.f, U.f, vw, gLo, gUp);
+#elif DN_T3_ORDER == 0
+    const float2 E = F::elem_pair(k, L.u, U.u, L.n, U.n, L.f, U.f, vw, gLo, gUp);
+#else
+    // the lower faces die in the z-stage: the plane after U is fetched into their registers BEFORE the
+    // modal arithmetic, in one basic block with it, so that the load/mask/x-y-stage instructions (LSU, ALU)
+    // fill the issue slots the packed FMA-pipe instructions leave free
+    typename F::Modes M;
+    F::zstage(L.u, U.u, L.n, U.n, L.f, U.f, M);
+    const float2 keepL0 = L.keep;
+    bool early = false;
+    if constexpr (DN_T3_ORDER == 1) early = true;
+    else early = ((warp >> 2) & 1) != 0;
+    if (early && s + 2 <= zl) load_next(L);
+    const float2 E = F::elem_modes(k, M, vw, gLo, gUp);
+#endif
     const float wl = (!resid && (unsigned)(sl - elo) < (unsigned)ecnt) ? ew : 0.f;
     e32 = fmaf(wl, E.x + E.y, e32);
     const RowG lo = face_to_rows(gLo);
@@ -564,8 +615,16 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     up = face_to_rows(gUp);
     const float2 Na01 = publish(done, po);
     arrive();              // this warp has read the stage of the U plane and published its sums of the L plane
+#if DN_T3_ORDER == 3
+    const float2 keepL = L.keep;
+    if (!late && s + 2 <= zl) load_next(L);
+#elif DN_T3_ORDER == 0
     const float2 keepL = L.keep;
     if (s + 2 <= zl) load_next(L);      // the plane after U replaces L in registers
+#else
+    const float2 keepL = keepL0;
+    if (!early && s + 2 <= zl) load_next(L);
+#endif
     wait_all();            // every warp has arrived: partial sums visible, the oldest stage is free
     refill();
     if constexpr (LK) finalize(Na01, keepL, po, pl >= z0 && pl < z1);
