@@ -228,6 +228,51 @@ def time_workload(name, dev, seed, K, W, reps, world=1, barrier=None, use_graph=
     return {"ms_step": ms_step, "mode": mode, "sets": sets, "fem": fem, "nsets": nsets}
 
 
+def copy_reference(dev, nbytes, K=50, reps=3):
+    """What a plain device copy achieves at THIS launch size: `b.copy_(a)` moving `nbytes` in total
+    (nbytes/2 read + nbytes/2 written -- the same definition as MEASURED_PEAKS.json's hbm_gbs, which is
+    taken at 4 GiB per launch), K launches replayed from one CUDA graph over rotating buffers larger
+    than the L2, CUDA events.  The fixed per-launch cost (launch, ramp-up, drain) that separates a
+    100 MB launch from the multi-GiB steady state is in this number too: it is the practical
+    ceiling of a single fused launch of that size, reported next to the roofline fraction."""
+    import torch
+    n = max(1, nbytes // 8)                       # floats per buffer
+    nsets = min(32, max(2, int(-(-400e6 // nbytes))))
+    a = [torch.empty(n, device=dev, dtype=torch.float32).normal_() for _ in range(nsets)]
+    b = [torch.empty(n, device=dev, dtype=torch.float32) for _ in range(nsets)]
+    for i in range(3):
+        b[i % nsets].copy_(a[i % nsets])
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        b[0].copy_(a[0])
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for i in range(K):
+            b[i % nsets].copy_(a[i % nsets])
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / K)
+    ms = sorted(ts)[len(ts) // 2]
+    peak, _ = measured_peak_gbs()
+    gbs = 2 * n * 4 / (ms * 1e-3) / 1e9
+    del a, b
+    torch.cuda.empty_cache()
+    return {"ms_per_launch": ms, "achieved": gbs, "unit": "GB/s", "frac_of_peak": gbs / peak, "bytes_per_launch": 2 * n * 4,
+            "what": "torch copy_ of the same number of bytes per launch (half read, half written), graph-replayed"}
+
+
 def time_ops(name, dev, K, reps=3):
     """The path's other operators at a BASELINE shape: the residual-minimisation form
     (forward operator pass + the backward operator pass, `resmin*`) and the un-fused
@@ -527,6 +572,12 @@ def run_ours(args):
     e2e_val = dof_step * world * Ke / float(te.item()) / 1e9
     del sets, res, devbuf, host, hs
     torch.cuda.empty_cache()
+    copyref = None
+    if world == 1:
+        try:
+            copyref = copy_reference(dev, step_bytes)
+        except Exception as e:   # noqa: BLE001
+            copyref = {"error": f"{type(e).__name__}: {e}"}
     # ---- the other BASELINE configs and the north_star's named roofline points, measured the same way
     points = None
     if world == 1 and args.points and name == DEFAULT:
@@ -537,6 +588,11 @@ def run_ours(args):
                 r = time_workload(pn, dev, 4321, max(20, min(K, 100)), 5, 3)
                 points[pn] = point_of(pn, r, peak0)
                 del r
+                torch.cuda.empty_cache()
+                pnsd, psize, pB, pbpd, _ = WORKLOADS[pn]
+                cr = copy_reference(dev, pB * psize ** pnsd * pbpd)
+                points[pn]["roofline"]["same_bytes_copy"] = cr
+                points[pn]["roofline"]["frac_of_same_bytes_copy"] = points[pn]["roofline"]["achieved"] / cr["achieved"]
             except Exception as e:   # noqa: BLE001  (the headline must still be printed)
                 points[pn] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
@@ -602,6 +658,8 @@ def run_ours(args):
                          "traffic_note": tr.get("note"), "traffic_source": tr.get("source"),
                          "peak_source": peak_src, "bytes_per_dof": bpd,
                          "algorithmic_bytes_per_launch": step_bytes,
+                         "same_bytes_copy": copyref,
+                         "frac_of_same_bytes_copy": (achieved / copyref["achieved"]) if copyref and "achieved" in copyref else None,
                          "kernel": "k_fem2d_tma" if nsd == 2 else "k_fem3d_tma",
                          "secondary": {"bound": "fp32_pipe", "unit": "TFLOP/s",
                                        "achieved": value / world * FLOPS_PER_DOF[nsd] / 1e3, "peak": fp32_peak,

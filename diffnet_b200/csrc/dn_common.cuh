@@ -24,7 +24,7 @@ struct Mask {
 // and a fixed-order final sum done by whichever CTA draws the last ticket (bit-reproducible:
 // the order of the final sum depends only on the grid, never on arrival order).
 struct Reduce {
-  double* partials;      // [gridDim.x]
+  double* partials;      // [gridDim.x]; all-zero bits on entry and on exit (see finish_loss_w0, fem2d_tma.cuh)
   unsigned int* counter; // zero on entry, zero on exit
   double* loss_out;      // nullable
   float* loss_f32;       // nullable
@@ -72,7 +72,10 @@ __device__ __forceinline__ void finish_loss(const Reduce& r, double cta_value, d
   __threadfence();
   // fixed-order strided partial sums, then a fixed tree over warps
   double s = 0.0;
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(r.partials + i);
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    s += __ldcg(r.partials + i);
+    __stcg(r.partials + i, 0.0);     // the streaming kernels read an all-zero slot as "not yet written"
+  }
   s = warp_sum(s);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
   if (lane == 0) smem[warp] = s;

@@ -253,34 +253,62 @@ struct Fem2T {
   }
 };
 
-// Loss epilogue for the streaming kernels: only warp 0 takes part (the other warps retire at
-// once).  Thread 0 publishes the CTA partial and draws a ticket; the warp that draws the last
-// one sums all partials in a fixed order (lane-strided, then an xor butterfly): bit-reproducible.
-__device__ __forceinline__ void finish_loss_w0(const Reduce& r, double cta_value) {
+// Loss epilogue for the streaming kernels.  Only warp 0 takes part (the other warps retire at once) and
+// no CTA waits for a fence or an atomic round trip at its end:
+//   * at its START (after pdl_wait) thread 0 of every CTA draws a ticket (draw_start_ticket; the answer is
+//     not needed before the epilogue, so its latency hides behind the first tile loads).  The CTA that
+//     drew the LAST ticket is the finisher: every other CTA has started by then, so waiting for them
+//     cannot deadlock, and it is among the last to finish.
+//   * a CTA publishes its partial with ONE 8-byte store whose bit pattern is never zero (+-0.0 is stored
+//     as -0.0): the value is its own "ready" flag, so no fence / ticket separates data and flag.
+//   * the finisher polls the slots until none is zero (one batched L2 round trip per sweep), sums them in
+//     a fixed order (lane-strided, then an xor butterfly: bit-reproducible), and zeroes slots and counter
+//     again: the workspace contract (zero on entry, zero on exit) is unchanged.
+__device__ __forceinline__ unsigned int draw_start_ticket(const Reduce& r) { return atomicAdd(r.counter, 1u); }
+
+__device__ __forceinline__ long long ld_relaxed_b64(const void* p) {
+  long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// NB = slots per lane fetched per sweep (all of them are live registers while the sweep is checked)
+template <int NB = 40>
+__device__ __forceinline__ void finish_loss_w0(const Reduce& r, double cta_value, unsigned int start_ticket) {
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
-  unsigned last = 0u;
+  unsigned fin = 0u;
   if (lane == 0) {
-    __stcg(r.partials + blockIdx.x, cta_value);
-    __threadfence();
-    last = (atomicAdd(r.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    long long bits = __double_as_longlong(cta_value);
+    if ((bits << 1) == 0) bits = (long long)0x8000000000000000ull;      // +-0.0 -> -0.0: never the "empty" pattern
+    __stcg(reinterpret_cast<long long*>(r.partials + blockIdx.x), bits);
+    fin = (start_ticket == gridDim.x - 1) ? 1u : 0u;
   }
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return;
-  __threadfence();
+  fin = __shfl_sync(0xffffffffu, fin, 0);
+  if (!fin) return;
   const unsigned n = gridDim.x;
   double s = 0.0;
-  for (unsigned base = 0; base < n; base += 32 * 40) {   // up to 40 independent L2 loads per lane in flight
-    double v[40];
+  for (unsigned base = 0; base < n; base += 32 * NB) {   // up to NB independent L2 loads per lane in flight
+    long long v[NB];
+    bool all;
+    do {
+      all = true;
 #pragma unroll
-    for (int q = 0; q < 40; ++q) {
+      for (int q = 0; q < NB; ++q) {
+        const unsigned i = base + q * 32 + lane;
+        v[q] = (i < n) ? ld_relaxed_b64(r.partials + i) : (long long)0x8000000000000000ull;
+        all = all && (v[q] != 0);
+      }
+      all = __all_sync(0xffffffffu, all);
+    } while (!all);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
       const unsigned i = base + q * 32 + lane;
-      v[q] = (i < n) ? __ldcg(r.partials + i) : 0.0;
+      s += __longlong_as_double(v[q]);                    // out-of-range slots hold -0.0
+      if (i < n) __stcg(reinterpret_cast<long long*>(r.partials + i), 0ll);   // self-reset
     }
-#pragma unroll
-    for (int q = 0; q < 40; ++q) s += v[q];
   }
-  s = warp_sum(s);
+  s = warp_sum(s) + 0.0;                                  // -0.0 (all partials zero) -> +0.0
   if (r.peer_slots) {      // linked z-slab launch: push the rank total to every rank (NVLink stores), then the flags
     const int want = *r.step + 1;
     if (lane < r.world) {
@@ -306,6 +334,7 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
   constexpr int NF = F::NF;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[TB / 32];
+  __shared__ unsigned int s_ticket;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int nx = p.nx, S = p.S;
@@ -349,6 +378,7 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
     const int n0 = min(S, nst);
     for (int q = 0; q < n0; ++q) issue_stage();     // thread 0 only; the others just count
   }
+  if (tid == 0) s_ticket = draw_start_ticket(p.red);  // its round trip hides behind the first tile loads
   __syncthreads();                                   // barriers initialised before anyone waits
 
   const bool act = tid * 4 < nx;
@@ -452,7 +482,7 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
   double cta = 0.0;
   if (tid == 0)
     for (int w = 0; w < nw; ++w) cta += s_red[w];
-  finish_loss_w0(p.red, cta);
+  finish_loss_w0(p.red, cta, s_ticket);
 }
 
 // ---- dispatch (fem2d_tma_dispatch.cu) --------------------------------------------------------

@@ -472,7 +472,10 @@ __global__ void __launch_bounds__(DN_MAXT_3D) k_fem3d(const P3D p) {
     if (is_last) {
       __threadfence();
       double sacc = 0.0;
-      for (unsigned int i = tid; i < gridDim.x; i += nthreads) sacc += __ldcg(p.red.partials + i);
+      for (unsigned int i = tid; i < gridDim.x; i += nthreads) {
+        sacc += __ldcg(p.red.partials + i);
+        __stcg(p.red.partials + i, 0.0);     // zero on exit: the streaming kernels read zero as "not yet written"
+      }
       sacc = warp_sum(sacc);
       if (lane == 0) s_red[warp] = sacc;
       __syncthreads();

@@ -17,7 +17,7 @@
 //     y-stage per element face, z-stage per element.  The face below an element is the face above
 //     the previous one: it is carried in registers, so each plane is read once per thread.
 //     The transposed transform (modal gradient -> nodes) is hierarchical the same way and the
-//     z-carry of the gradient is kept in row (sum, difference) space.
+//     z-carry of the gradient is kept in face-mode space (one transposed y-stage per plane).
 //   * Gradient gather without atomics: per plane each thread publishes its lower-row partial sums
 //     to shared memory; after ONE __syncthreads (which also releases the consumed ring stage) the
 //     owner of each node row adds the three neighbour shares, masks Dirichlet nodes and stores.
@@ -357,6 +357,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   constexpr int NF = F::NF;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[DN_T3_MAXT / 32];
+  __shared__ unsigned int s_ticket;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction
@@ -376,6 +377,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     pdl_wait();
     want = *p.red.step + 1;
     if ((int)blockIdx.x < nputc) {
+      if (tid == 0) s_ticket = draw_start_ticket(p.red);
       const int side = (int)blockIdx.x / p.lk.nput, part = (int)blockIdx.x - side * p.lk.nput;
       if (p.lk.pdst[side]) {
         float4* dst = p.lk.pdst[side];
@@ -392,7 +394,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
           }
         }
       }
-      finish_loss_w0(p.red, 0.0);
+      finish_loss_w0<8>(p.red, 0.0, s_ticket);
       return;
     }
   }
@@ -466,6 +468,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     const int n0 = min(S, npl);
     for (int q = 0; q < n0; ++q) issue_plane();
   }
+  if (tid == 0) s_ticket = draw_start_ticket(p.red);   // its round trip hides behind the first plane loads
 
   // ---- thread geometry
   const int r_raw = tid / LXT, lx = tid - r_raw * LXT;
@@ -506,8 +509,8 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   // lower faces of the next (no copies)
   struct Plane { Face u, n, f; float2 keep; };
   Plane PA, PB;
-  RowG up;                                       // z-carry of the gradient (row space), upper plane
-  up.sa = up.da = up.sb = up.db = f2(0.f);
+  Face up;                                       // z-carry of the gradient (face-mode space), upper plane
+  up.m0 = up.m1 = up.m2 = up.m3 = f2(0.f);
   double acc = 0.0;
   float e32 = 0.f;
   int st = 0;
@@ -608,12 +611,11 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
 #endif
     const float wl = (!resid && (unsigned)(sl - elo) < (unsigned)ecnt) ? ew : 0.f;
     e32 = fmaf(wl, E.x + E.y, e32);
-    const RowG lo = face_to_rows(gLo);
-    RowG done;
-    done.sa = add2(up.sa, lo.sa); done.da = add2(up.da, lo.da);
-    done.sb = add2(up.sb, lo.sb); done.db = add2(up.db, lo.db);
-    up = face_to_rows(gUp);
-    const float2 Na01 = publish(done, po);
+    Face dF;                 // plane L is complete: carry from the layer below + this layer's lower face
+    dF.m0 = add2(up.m0, gLo.m0); dF.m1 = add2(up.m1, gLo.m1);
+    dF.m2 = add2(up.m2, gLo.m2); dF.m3 = add2(up.m3, gLo.m3);
+    up = gUp;
+    const float2 Na01 = publish(face_to_rows(dF), po);
     arrive();              // this warp has read the stage of the U plane and published its sums of the L plane
 #if DN_T3_ORDER == 3
     const float2 keepL = L.keep;
@@ -644,7 +646,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   // plane going down): no element layer beyond it
   if (rev ? (z0 == 0) : (z1 == p.nz)) {
     const uint32_t po = odd ? kPAR : 0u;
-    const float2 Na01 = publish(up, po);
+    const float2 Na01 = publish(face_to_rows(up), po);
     arrive();
     wait_all();
     finalize(Na01, odd ? PB.keep : PA.keep, po, true);
@@ -658,7 +660,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   double cta = 0.0;
   if (tid == 0)
     for (int w = 0; w < (NT >> 5); ++w) cta += s_red[w];
-  finish_loss_w0(p.red, cta);
+  finish_loss_w0<8>(p.red, cta, s_ticket);   // 3-D grids are a few hundred CTAs
 }
 
 // ---- dispatch (fem3d_tma_dispatch.cu) --------------------------------------------------------

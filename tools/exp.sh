@@ -1,5 +1,13 @@
-for lib in "" variants/lib_o3.so variants/lib_o2.so; do
-  echo "=== lib ${lib:-default}"
-  DIFFNET_FEM_LIB=${lib:+$PWD/$lib} python tools/sweep.py --graph --n 20 --cfg "DN_T3_THREADS=256" --cfg "DN_T3_THREADS=384" poisson3d_256_b1 poisson3d_128_b1 poisson3d_param_64_b16 2>&1 | grep -v Warning
-done
-DIFFNET_FEM_LIB=$PWD/variants/lib_o3.so python -m pytest tests/test_gpu_parity_3d.py -m gpu -x -q 2>&1 | tail -3
+# scratch experiment driver (one gpurun call)
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for i in 1 2; do python -m pytest tests -m gpu -x -q 2>&1 | tail -1; done
+python bench.py --no-cpu --train-steps 0 > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err; echo "bench rc=$?"
+python tools/show_bench.py gpurun_out/r2b_bench.json | head -16
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2b_bench.json').read().strip().splitlines()[-1])
+print('copy ref default:', d['roofline'].get('same_bytes_copy'), d['roofline'].get('frac_of_same_bytes_copy'))
+for k,v in d['points'].items():
+    if 'roofline' in v and 'same_bytes_copy' in v['roofline']:
+        c=v['roofline']['same_bytes_copy']; print(k, 'copy %.1f us frac %.3f -> ours/copy %.3f'%(c['ms_per_launch']*1e3, c['frac_of_peak'], v['roofline']['frac_of_same_bytes_copy']))
+PY
