@@ -53,6 +53,8 @@ _RESID_ARGS = [_P(dn_field), _P(dn_field), _P(dn_field), _P(dn_mask), C.c_int, C
                C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
 _GP_ARGS = [_P(dn_field), _P(dn_geom), C.c_int, C.c_void_p, C.c_void_p]
 _GPADJ_ARGS = [C.c_void_p, _P(dn_geom), C.c_int, C.c_void_p, C.c_void_p]
+_GPM_ARGS = [_P(dn_field), _P(dn_geom), C.c_int, _P(C.c_int), _P(C.c_void_p), C.c_void_p]
+_GPMADJ_ARGS = [_P(C.c_void_p), _P(dn_geom), C.c_int, _P(C.c_int), C.c_void_p, C.c_void_p]
 
 # symbol -> (restype, argtypes); tests/test_abi.py checks this table against include/diffnet_fem.h
 PROTOTYPES = {
@@ -75,6 +77,10 @@ PROTOTYPES = {
     "dn_fem_gp_eval_3d_f32": (C.c_int, _GP_ARGS),
     "dn_fem_gp_eval_adj_2d_f32": (C.c_int, _GPADJ_ARGS),
     "dn_fem_gp_eval_adj_3d_f32": (C.c_int, _GPADJ_ARGS),
+    "dn_fem_gp_eval_multi_2d_f32": (C.c_int, _GPM_ARGS),
+    "dn_fem_gp_eval_multi_3d_f32": (C.c_int, _GPM_ARGS),
+    "dn_fem_gp_eval_multi_adj_2d_f32": (C.c_int, _GPMADJ_ARGS),
+    "dn_fem_gp_eval_multi_adj_3d_f32": (C.c_int, _GPMADJ_ARGS),
     "dn_scale_inplace_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "dn_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "dn_peer_free": (C.c_int, [C.c_void_p]),

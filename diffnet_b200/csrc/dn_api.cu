@@ -514,44 +514,65 @@ static int gp_common(const dn_geom* g, int which, int nsd, GpTables* tb) {
   return DN_OK;
 }
 
-int dn_fem_gp_eval_2d_f32(const dn_field* in, const dn_geom* g, int which, float* out,
-                          void* stream) {
+static int gp_forward(const dn_field* in, const dn_geom* g, int nsd, int nwhich, const int* which,
+                      float* const* outs, void* stream) {
   if (int rc = device_ok(nullptr)) return rc;
-  GpTables tb;
-  if (int rc = gp_common(g, which, 2, &tb)) return rc;
-  if (!in || !in->ptr || !out) return fail(DN_EINVAL, "NULL input/output");
-  return check_cuda(launch_gp_eval(to_field(in), g->batch, g->nx, g->ny, 1, 2, tb, out,
+  if (nwhich < 1 || nwhich > 4 || !which || !outs) return fail(DN_EINVAL, "1..4 tables per call");
+  GpMulti m;
+  m.nw = nwhich;
+  for (int w = 0; w < nwhich; ++w) {
+    if (int rc = gp_common(g, which[w], nsd, &m.tb[w])) return rc;
+    if (!outs[w]) return fail(DN_EINVAL, "NULL output %d", w);
+    m.out[w] = outs[w];
+  }
+  if (!in || !in->ptr) return fail(DN_EINVAL, "NULL input");
+  return check_cuda(launch_gp_eval(to_field(in), g->batch, g->nx, g->ny, nsd == 3 ? g->nz : 1, nsd, m,
                                    (cudaStream_t)stream), "gp_eval launch");
 }
 
-int dn_fem_gp_eval_3d_f32(const dn_field* in, const dn_geom* g, int which, float* out,
-                          void* stream) {
+static int gp_adjoint(const float* const* grad_outs, const dn_geom* g, int nsd, int nwhich, const int* which,
+                      float* grad_in, void* stream) {
   if (int rc = device_ok(nullptr)) return rc;
-  GpTables tb;
-  if (int rc = gp_common(g, which, 3, &tb)) return rc;
-  if (!in || !in->ptr || !out) return fail(DN_EINVAL, "NULL input/output");
-  return check_cuda(launch_gp_eval(to_field(in), g->batch, g->nx, g->ny, g->nz, 3, tb, out,
-                                   (cudaStream_t)stream), "gp_eval launch");
-}
-
-int dn_fem_gp_eval_adj_2d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in,
-                              void* stream) {
-  if (int rc = device_ok(nullptr)) return rc;
-  GpTables tb;
-  if (int rc = gp_common(g, which, 2, &tb)) return rc;
-  if (!grad_out || !grad_in) return fail(DN_EINVAL, "NULL input/output");
-  return check_cuda(launch_gp_eval_adj(grad_out, g->batch, g->nx, g->ny, 1, 2, tb, grad_in,
+  if (nwhich < 1 || nwhich > 4 || !which || !grad_outs) return fail(DN_EINVAL, "1..4 tables per call");
+  GpMultiAdj m;
+  m.nw = nwhich;
+  for (int w = 0; w < nwhich; ++w) {
+    if (int rc = gp_common(g, which[w], nsd, &m.tb[w])) return rc;
+    if (!grad_outs[w]) return fail(DN_EINVAL, "NULL cotangent %d", w);
+    m.gout[w] = grad_outs[w];
+  }
+  if (!grad_in) return fail(DN_EINVAL, "NULL output");
+  return check_cuda(launch_gp_eval_adj(g->batch, g->nx, g->ny, nsd == 3 ? g->nz : 1, nsd, m, grad_in,
                                        (cudaStream_t)stream), "gp_eval_adj launch");
 }
 
-int dn_fem_gp_eval_adj_3d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in,
-                              void* stream) {
-  if (int rc = device_ok(nullptr)) return rc;
-  GpTables tb;
-  if (int rc = gp_common(g, which, 3, &tb)) return rc;
-  if (!grad_out || !grad_in) return fail(DN_EINVAL, "NULL input/output");
-  return check_cuda(launch_gp_eval_adj(grad_out, g->batch, g->nx, g->ny, g->nz, 3, tb, grad_in,
-                                       (cudaStream_t)stream), "gp_eval_adj launch");
+int dn_fem_gp_eval_2d_f32(const dn_field* in, const dn_geom* g, int which, float* out, void* stream) {
+  return gp_forward(in, g, 2, 1, &which, &out, stream);
+}
+int dn_fem_gp_eval_3d_f32(const dn_field* in, const dn_geom* g, int which, float* out, void* stream) {
+  return gp_forward(in, g, 3, 1, &which, &out, stream);
+}
+int dn_fem_gp_eval_adj_2d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in, void* stream) {
+  return gp_adjoint(&grad_out, g, 2, 1, &which, grad_in, stream);
+}
+int dn_fem_gp_eval_adj_3d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in, void* stream) {
+  return gp_adjoint(&grad_out, g, 3, 1, &which, grad_in, stream);
+}
+int dn_fem_gp_eval_multi_2d_f32(const dn_field* in, const dn_geom* g, int nwhich, const int* which,
+                                float* const* outs, void* stream) {
+  return gp_forward(in, g, 2, nwhich, which, outs, stream);
+}
+int dn_fem_gp_eval_multi_3d_f32(const dn_field* in, const dn_geom* g, int nwhich, const int* which,
+                                float* const* outs, void* stream) {
+  return gp_forward(in, g, 3, nwhich, which, outs, stream);
+}
+int dn_fem_gp_eval_multi_adj_2d_f32(const float* const* grad_outs, const dn_geom* g, int nwhich, const int* which,
+                                    float* grad_in, void* stream) {
+  return gp_adjoint(grad_outs, g, 2, nwhich, which, grad_in, stream);
+}
+int dn_fem_gp_eval_multi_adj_3d_f32(const float* const* grad_outs, const dn_geom* g, int nwhich, const int* which,
+                                    float* grad_in, void* stream) {
+  return gp_adjoint(grad_outs, g, 3, nwhich, which, grad_in, stream);
 }
 
 int dn_peer_alloc(size_t bytes, void** ptr) {

@@ -1,105 +1,154 @@
 // gp_eval.cu -- see gp_eval.cuh.
+//
+// Un-fused gauss_pt_evaluation* (DiffNet/DiffNetFEM.py:7-18,143-156) and its adjoint for user loss() bodies that
+// are not one of the fused forms.  Both are pure streaming operators: the forward writes ngp values per element
+// and table (write-bound: 4 B read, 4 ngp B written per node), the adjoint reads them back (read-bound).
+//
+//   * A thread owns one element column (forward) / node column (adjoint) and MARCHES in y: the node row shared by
+//     two element rows is loaded once and kept in registers, element rows contribute to the node rows above and
+//     below through a register carry.  Lanes run along x: every load and store instruction of a warp covers 32
+//     consecutive floats.  No integer division in the loop (the grid is (x chunks, y chunks, plane * batch)).
+//   * All requested tables (N, d/dx, d/dy, d/dz) are evaluated in ONE pass over the input (GpMulti): a loss body
+//     that needs u, u_x, u_y at the Gauss points streams u once instead of three times.
+//   * Outputs are write-once: streaming stores (st.global.cs), so they do not evict the inputs from L2.
+//   * Adjoint: the x-neighbour's share travels by one warp shuffle per node row; a warp covers 31 node columns
+//     plus one provider lane on its left, so there are no shared-memory seams and no atomics (deterministic).
 #include "gp_eval.cuh"
 
 namespace dn {
 
-// out[b, G, (k,) j, i] = sum_a T[G][a] * in[b, (k+kb,) j+jb, i+ib],  G = (kg*n + jg)*n + ig.
-// One thread per element, x fastest (coalesced loads and stores); each nodal value is read
-// by the 4 (8) elements around it through L1.
-template <int NSD>
-__global__ void __launch_bounds__(256) k_gp_eval(Field in, int B, int nx, int ny, int nz,
-                                                 GpTables tb, float* __restrict__ out) {
+constexpr int kGpThreads = 128;
+
+// ---- forward ---------------------------------------------------------------------------------------------------
+// out_w[b, G, (k,) j, i] = sum_a T_w[G][a] * in[b, (k+kb,) j+jb, i+ib],  G = (kg*n + jg)*n + ig.
+template <int NSD, int NG>
+__global__ void __launch_bounds__(kGpThreads) k_gp_eval(Field in, int nx, int ny, int nz, GpMulti m, int RY) {
+  constexpr int NZ = (NSD == 3) ? 2 : 1;
+  constexpr int NGP = (NSD == 3) ? NG * NG * NG : NG * NG;
   const int nelx = nx - 1, nely = ny - 1, nelz = (NSD == 3) ? nz - 1 : 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelx) return;
+  const int j0 = blockIdx.y * RY, j1 = min(nely, j0 + RY);
+  const int k = (NSD == 3) ? (int)(blockIdx.z % nelz) : 0;
+  const int b = (NSD == 3) ? (int)(blockIdx.z / nelz) : (int)blockIdx.z;
   const long long nel = (long long)nelx * nely * nelz;
-  const long long total = nel * B;
-  const int n = tb.n;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(idx % nelx);
-    long long r = idx / nelx;
-    const int j = (int)(r % nely);
-    r /= nely;
-    const int k = (int)(r % nelz);
-    const int b = (int)(r / nelz);
-    const float* base = in.p + (long long)b * in.sb + (long long)k * (NSD == 3 ? in.sz : 0) +
-                        (long long)j * in.sy + i;
-    float v[2][2][2];
+  const float* base = in.p + (long long)b * in.sb + (NSD == 3 ? (long long)k * in.sz : 0) + (long long)j0 * in.sy + i;
+  const long long obase = (long long)b * NGP * nel + ((long long)k * nely + j0) * nelx + i;
+
+  float v[NZ][2][2];       // [kb][jb][ib]
 #pragma unroll
-    for (int kb = 0; kb < (NSD == 3 ? 2 : 1); ++kb)
+  for (int kb = 0; kb < NZ; ++kb) {
+    const float* q = base + (long long)kb * in.sz;
+    v[kb][1][0] = __ldg(q);
+    v[kb][1][1] = __ldg(q + 1);
+  }
+  for (int j = j0; j < j1; ++j) {
+    base += in.sy;
 #pragma unroll
-      for (int jb = 0; jb < 2; ++jb)
+    for (int kb = 0; kb < NZ; ++kb) {
+      const float* q = base + (long long)kb * in.sz;
+      v[kb][0][0] = v[kb][1][0]; v[kb][0][1] = v[kb][1][1];
+      v[kb][1][0] = __ldg(q);
+      v[kb][1][1] = __ldg(q + 1);
+    }
+    const long long orow = obase + (long long)(j - j0) * nelx;
 #pragma unroll
-        for (int ib = 0; ib < 2; ++ib)
-          v[kb][jb][ib] = __ldg(base + (long long)kb * in.sz + (long long)jb * in.sy + ib);
-    float* o = out + (long long)b * (NSD == 3 ? n * n * n : n * n) * nel +
-               ((long long)k * nely + j) * nelx + i;
-    for (int kg = 0; kg < (NSD == 3 ? n : 1); ++kg) {
-      // collapse z
-      float w[2][2];
+    for (int w = 0; w < 4; ++w) {
+      if (w >= m.nw) break;
+      const GpTables& tb = m.tb[w];
+      float* o = m.out[w] + orow;
 #pragma unroll
-      for (int jb = 0; jb < 2; ++jb)
+      for (int kg = 0; kg < (NSD == 3 ? NG : 1); ++kg) {
+        float wz[2][2];
 #pragma unroll
-        for (int ib = 0; ib < 2; ++ib)
-          w[jb][ib] = (NSD == 3) ? tb.c[2][kg][0] * v[0][jb][ib] + tb.c[2][kg][1] * v[1][jb][ib]
-                                 : v[0][jb][ib];
-      for (int jg = 0; jg < n; ++jg) {
-        const float r0 = tb.c[1][jg][0] * w[0][0] + tb.c[1][jg][1] * w[1][0];
-        const float r1 = tb.c[1][jg][0] * w[0][1] + tb.c[1][jg][1] * w[1][1];
-        for (int ig = 0; ig < n; ++ig) {
-          const int G = (kg * n + jg) * n + ig;
-          o[(long long)G * nel] = tb.c[0][ig][0] * r0 + tb.c[0][ig][1] * r1;
+        for (int jb = 0; jb < 2; ++jb)
+#pragma unroll
+          for (int ib = 0; ib < 2; ++ib)
+            wz[jb][ib] = (NSD == 3) ? tb.c[2][kg][0] * v[0][jb][ib] + tb.c[2][kg][1] * v[NZ - 1][jb][ib] : v[0][jb][ib];
+#pragma unroll
+        for (int jg = 0; jg < NG; ++jg) {
+          const float r0 = tb.c[1][jg][0] * wz[0][0] + tb.c[1][jg][1] * wz[1][0];
+          const float r1 = tb.c[1][jg][0] * wz[0][1] + tb.c[1][jg][1] * wz[1][1];
+#pragma unroll
+          for (int ig = 0; ig < NG; ++ig) {
+            const int G = (kg * NG + jg) * NG + ig;
+            __stcs(o + (long long)G * nel, tb.c[0][ig][0] * r0 + tb.c[0][ig][1] * r1);
+          }
         }
       }
     }
   }
 }
 
-// gin[b, node] = sum over the elements e around the node and all Gauss points G of
-// T[G][a(node in e)] * gout[b, G, e]  (gather form: no atomics, deterministic).
-template <int NSD>
-__global__ void __launch_bounds__(256) k_gp_eval_adj(const float* __restrict__ gout, int B, int nx,
-                                                     int ny, int nz, GpTables tb,
-                                                     float* __restrict__ gin) {
+// ---- adjoint ---------------------------------------------------------------------------------------------------
+// gin[b, node] = sum_w sum over the elements e around the node and all Gauss points G of
+//                T_w[G][a(node in e)] * gout_w[b, G, e]          (gather form: no atomics, deterministic).
+// Lane l of a warp works on element column e = xw - 1 + l and (for l >= 1) stores node column x = e.
+template <int NSD, int NG>
+__global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx, int ny, int nz, int RY,
+                                                            float* __restrict__ gin) {
+  constexpr int NZ = (NSD == 3) ? 2 : 1;
+  constexpr int NGP = (NSD == 3) ? NG * NG * NG : NG * NG;
   const int nelx = nx - 1, nely = ny - 1, nelz = (NSD == 3) ? nz - 1 : 1;
   const int nzz = (NSD == 3) ? nz : 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int xw = (blockIdx.x * (blockDim.x >> 5) + warp) * 31;          // first node column of this warp
+  if (xw >= nx) return;                                                  // warp-uniform
+  const int e = xw - 1 + lane;                                           // element column of this lane
+  const bool ev = (e >= 0) && (e < nelx);
+  const int x = e;                                                       // node column stored by lanes >= 1
+  const bool sv = (lane >= 1) && (x < nx);
+  const int y0 = blockIdx.y * RY, y1 = min(ny, y0 + RY);                 // node rows [y0, y1)
+  const int z = (NSD == 3) ? (int)(blockIdx.z % nzz) : 0;
+  const int b = (NSD == 3) ? (int)(blockIdx.z / nzz) : (int)blockIdx.z;
   const long long nel = (long long)nelx * nely * nelz;
-  const long long total = (long long)B * nzz * ny * nx;
-  const int n = tb.n;
-  const int ngp = (NSD == 3) ? n * n * n : n * n;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % nx);
-    long long r = idx / nx;
-    const int y = (int)(r % ny);
-    r /= ny;
-    const int z = (int)(r % nzz);
-    const int b = (int)(r / nzz);
-    const float* gb = gout + (long long)b * ngp * nel;
-    float acc = 0.f;
-    for (int kb = 0; kb < (NSD == 3 ? 2 : 1); ++kb) {
-      const int ek = z - kb;
-      if (NSD == 3 && (ek < 0 || ek >= nelz)) continue;
-      for (int jb = 0; jb < 2; ++jb) {
-        const int ej = y - jb;
-        if (ej < 0 || ej >= nely) continue;
-        for (int ib = 0; ib < 2; ++ib) {
-          const int ei = x - ib;
-          if (ei < 0 || ei >= nelx) continue;
-          const float* ge = gb + ((long long)(NSD == 3 ? ek : 0) * nely + ej) * nelx + ei;
-          for (int kg = 0; kg < (NSD == 3 ? n : 1); ++kg) {
+  const long long gb = (long long)b * NGP * nel + (ev ? e : 0);
+  float* orow = gin + (((long long)b * nzz + z) * ny + y0) * nx + (sv ? x : 0);
+
+  float carry = 0.f;                      // contribution of element row ej - 1 to node row ej (jb = 1), own + left share
+  for (int ej = y0 - 1; ej < y1; ++ej) {
+    // Q[jb][ib]: this element column's contribution (both layers around plane z, all tables) to its node
+    // row jb (0: row ej, 1: row ej + 1) and node column ib (0: x = e, 1: x = e + 1)
+    float Q[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    if (ev && ej >= 0 && ej < nely) {
+#pragma unroll
+      for (int kb = 0; kb < NZ; ++kb) {
+        const int ek = z - kb;
+        if (NSD == 3 && (ek < 0 || ek >= nelz)) continue;
+        const long long eoff = gb + ((long long)(NSD == 3 ? ek : 0) * nely + ej) * nelx;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          if (w >= m.nw) break;
+          const GpTables& tb = m.tb[w];
+          const float* ge = m.gout[w] + eoff;
+#pragma unroll
+          for (int kg = 0; kg < (NSD == 3 ? NG : 1); ++kg) {
             const float cz = (NSD == 3) ? tb.c[2][kg][kb] : 1.f;
-            for (int jg = 0; jg < n; ++jg) {
-              const float czy = cz * tb.c[1][jg][jb];
-              float s = 0.f;
-              for (int ig = 0; ig < n; ++ig)
-                s += tb.c[0][ig][ib] * __ldg(ge + (long long)((kg * n + jg) * n + ig) * nel);
-              acc += czy * s;
+#pragma unroll
+            for (int jg = 0; jg < NG; ++jg) {
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int ig = 0; ig < NG; ++ig) {
+                const float gv = __ldg(ge + (long long)((kg * NG + jg) * NG + ig) * nel);
+                s0 += tb.c[0][ig][0] * gv;
+                s1 += tb.c[0][ig][1] * gv;
+              }
+              const float c0 = cz * tb.c[1][jg][0], c1 = cz * tb.c[1][jg][1];
+              Q[0][0] += c0 * s0; Q[0][1] += c0 * s1;
+              Q[1][0] += c1 * s0; Q[1][1] += c1 * s1;
             }
           }
         }
       }
     }
-    gin[idx] = acc;
+    // node (ej, x): own element's (jb = 0, ib = 0) + left element's (jb = 0, ib = 1) + the carry of row ej - 1
+    const float l0 = __shfl_up_sync(0xffffffffu, Q[0][1], 1);
+    const float l1 = __shfl_up_sync(0xffffffffu, Q[1][1], 1);
+    if (ej >= y0) {
+      if (sv) __stcs(orow, carry + Q[0][0] + l0);
+      orow += nx;
+    }
+    carry = Q[1][0] + l1;
   }
 }
 
@@ -119,34 +168,99 @@ __global__ void __launch_bounds__(256) k_scale(float* __restrict__ x, size_t n,
     x[i] *= f;
 }
 
-static int grid_for(long long total, int block) {
-  long long g = (total + block - 1) / block;
-  const long long cap = 148LL * 16;
-  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+static int sm_count() {
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!sms[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    sms[dev] = n;
+  }
+  return sms[dev];
 }
 
-cudaError_t launch_gp_eval(Field in, int B, int nx, int ny, int nz, int nsd, const GpTables& tb,
-                           float* out, cudaStream_t s) {
-  const long long total = (long long)B * (nx - 1) * (ny - 1) * (nsd == 3 ? nz - 1 : 1);
-  if (nsd == 2)
-    k_gp_eval<2><<<grid_for(total, 256), 256, 0, s>>>(in, B, nx, ny, 1, tb, out);
-  else
-    k_gp_eval<3><<<grid_for(total, 256), 256, 0, s>>>(in, B, nx, ny, nz, tb, out);
+// Rows per chunk: long enough that the re-read halo row is cheap (1/RY), short enough that the grid has
+// several CTAs per SM slot.
+static int rows_per_chunk(long long columns_ctas, int rows) {
+  const long long want = 8LL * sm_count();                 // CTAs in the grid
+  long long chunks = (want + columns_ctas - 1) / columns_ctas;
+  if (chunks < 1) chunks = 1;
+  int ry = (int)((rows + chunks - 1) / chunks);
+  if (ry < 8) ry = 8;
+  if (ry > rows) ry = rows;
+  return ry < 1 ? 1 : ry;
+}
+
+template <int NSD>
+static cudaError_t launch_fwd(Field in, int B, int nx, int ny, int nz, GpMulti m, cudaStream_t s) {
+  const int nelx = nx - 1, nely = ny - 1, nelz = (NSD == 3) ? nz - 1 : 1;
+  const int NG = m.tb[0].n;
+  const long long per_b = (long long)(NSD == 3 ? NG * NG * NG : NG * NG) * nelx * nely * nelz;
+  const int threads = nelx >= kGpThreads ? kGpThreads : ((nelx + 31) / 32) * 32;
+  const int gx = (nelx + threads - 1) / threads;
+  const int bmax = 65535 / nelz;                       // gridDim.z = batch slice * element layers
+  if (bmax < 1) return cudaErrorInvalidConfiguration;
+  for (int b0 = 0; b0 < B; b0 += bmax) {
+    const int nb = (B - b0 < bmax) ? B - b0 : bmax;
+    const long long gz = (long long)nb * nelz;
+    const int RY = rows_per_chunk((long long)gx * gz, nely);
+    dim3 grid(gx, (nely + RY - 1) / RY, (unsigned)gz);
+    switch (NG) {
+      case 2: k_gp_eval<NSD, 2><<<grid, threads, 0, s>>>(in, nx, ny, nz, m, RY); break;
+      case 3: k_gp_eval<NSD, 3><<<grid, threads, 0, s>>>(in, nx, ny, nz, m, RY); break;
+      case 4: k_gp_eval<NSD, 4><<<grid, threads, 0, s>>>(in, nx, ny, nz, m, RY); break;
+      default: return cudaErrorInvalidValue;
+    }
+    in.p += (long long)nb * in.sb;
+    for (int w = 0; w < m.nw; ++w) m.out[w] += (long long)nb * per_b;
+  }
   return cudaGetLastError();
 }
 
-cudaError_t launch_gp_eval_adj(const float* gout, int B, int nx, int ny, int nz, int nsd,
-                               const GpTables& tb, float* gin, cudaStream_t s) {
-  const long long total = (long long)B * nx * ny * (nsd == 3 ? nz : 1);
-  if (nsd == 2)
-    k_gp_eval_adj<2><<<grid_for(total, 256), 256, 0, s>>>(gout, B, nx, ny, 1, tb, gin);
-  else
-    k_gp_eval_adj<3><<<grid_for(total, 256), 256, 0, s>>>(gout, B, nx, ny, nz, tb, gin);
+cudaError_t launch_gp_eval(Field in, int B, int nx, int ny, int nz, int nsd, const GpMulti& m, cudaStream_t s) {
+  return nsd == 2 ? launch_fwd<2>(in, B, nx, ny, 1, m, s) : launch_fwd<3>(in, B, nx, ny, nz, m, s);
+}
+
+template <int NSD>
+static cudaError_t launch_adj(int B, int nx, int ny, int nz, GpMultiAdj m, float* gin, cudaStream_t s) {
+  const int nzz = (NSD == 3) ? nz : 1;
+  const int nelx = nx - 1, nely = ny - 1, nelz = (NSD == 3) ? nz - 1 : 1;
+  const int NG = m.tb[0].n;
+  const long long per_b = (long long)(NSD == 3 ? NG * NG * NG : NG * NG) * nelx * nely * nelz;
+  const int warps_needed = (nx + 30) / 31;
+  const int wpc = warps_needed >= kGpThreads / 32 ? kGpThreads / 32 : warps_needed;
+  const int gx = (warps_needed + wpc - 1) / wpc;
+  const int bmax = 65535 / nzz;
+  if (bmax < 1) return cudaErrorInvalidConfiguration;
+  for (int b0 = 0; b0 < B; b0 += bmax) {
+    const int nb = (B - b0 < bmax) ? B - b0 : bmax;
+    const long long gz = (long long)nb * nzz;
+    const int RY = rows_per_chunk((long long)gx * gz, ny);
+    dim3 grid(gx, (ny + RY - 1) / RY, (unsigned)gz);
+    switch (NG) {
+      case 2: k_gp_eval_adj<NSD, 2><<<grid, wpc * 32, 0, s>>>(m, nx, ny, nz, RY, gin); break;
+      case 3: k_gp_eval_adj<NSD, 3><<<grid, wpc * 32, 0, s>>>(m, nx, ny, nz, RY, gin); break;
+      case 4: k_gp_eval_adj<NSD, 4><<<grid, wpc * 32, 0, s>>>(m, nx, ny, nz, RY, gin); break;
+      default: return cudaErrorInvalidValue;
+    }
+    gin += (long long)nb * nzz * ny * nx;
+    for (int w = 0; w < m.nw; ++w) m.gout[w] += (long long)nb * per_b;
+  }
   return cudaGetLastError();
+}
+
+cudaError_t launch_gp_eval_adj(int B, int nx, int ny, int nz, int nsd, const GpMultiAdj& m, float* gin,
+                               cudaStream_t s) {
+  return nsd == 2 ? launch_adj<2>(B, nx, ny, 1, m, gin, s) : launch_adj<3>(B, nx, ny, nz, m, gin, s);
 }
 
 cudaError_t launch_scale(float* x, size_t n, const float* factor_dev, cudaStream_t s) {
-  k_scale<<<grid_for((long long)(n + 3) / 4, 256), 256, 0, s>>>(x, n, factor_dev);
+  long long g = ((long long)(n + 3) / 4 + 255) / 256;
+  const long long cap = 16LL * sm_count();
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  k_scale<<<(int)g, 256, 0, s>>>(x, n, factor_dev);
   return cudaGetLastError();
 }
 

@@ -14,10 +14,21 @@ struct GpTables {
   float c[3][4][2];
 };
 
-cudaError_t launch_gp_eval(Field in, int B, int nx, int ny, int nz, int nsd, const GpTables& tb,
-                           float* out, cudaStream_t s);
-cudaError_t launch_gp_eval_adj(const float* gout, int B, int nx, int ny, int nz, int nsd,
-                               const GpTables& tb, float* gin, cudaStream_t s);
+// Up to four tables evaluated in one pass over the input (N, d/dx, d/dy, d/dz in any subset / order).
+struct GpMulti {
+  int nw;
+  GpTables tb[4];
+  float* out[4];          // each dense (B, ngp, [nz-1,] ny-1, nx-1)
+};
+struct GpMultiAdj {
+  int nw;
+  GpTables tb[4];
+  const float* gout[4];   // cotangents of the outputs above
+};
+
+cudaError_t launch_gp_eval(Field in, int B, int nx, int ny, int nz, int nsd, const GpMulti& m, cudaStream_t s);
+cudaError_t launch_gp_eval_adj(int B, int nx, int ny, int nz, int nsd, const GpMultiAdj& m, float* gin,
+                               cudaStream_t s);
 cudaError_t launch_scale(float* x, size_t n, const float* factor_dev, cudaStream_t s);
 
 }  // namespace dn

@@ -197,6 +197,12 @@ class DiffNetFEM(PDE):
             raise ValueError("gauss_pt_evaluation_der_z needs nsd == 3")
         return ops.gp_eval(self.geometry, tensor, "dz")
 
+    def gauss_pt_evaluation_all(self, tensor, which=None):
+        """(gauss_pt_evaluation(t), _der_x(t), _der_y(t)[, _der_z(t)]) from ONE pass over `t` (new; the
+        reference makes one conv sweep per table, DiffNetFEM.py:143-156)."""
+        which = which or (("N", "dx", "dy") + (("dz",) if self.nsd == 3 else ()))
+        return ops.gp_eval_multi(self.geometry, tensor, which)
+
     # ---------------------------------------------------------------- fused ops (new)
     def energy_loss(self, u, nu=None, f=None, f_gp=None, dirichlet=(), nu_zero_mask=None,
                     c_k=1.0, c_f=1.0, scale=1.0, reduction="mean"):

@@ -473,6 +473,57 @@ class GaussPointEvalFunction(torch.autograd.Function):
         return _like_input(gin, ctx.t_ref, geom), None, None
 
 
+def _gp_multi_raw(geom: Geometry, t: torch.Tensor, whichs: Sequence[int]):
+    """Several tables in one pass over `t` (dn_fem_gp_eval_multi_*): a tuple of (B, ngp, elems) tensors."""
+    tc = _canon(t, geom, "tensor")
+    B = tc.shape[0]
+    g = _geom_struct(geom, B)
+    outs = [_new_out((B, geom.ngp_1d ** geom.nsd) + geom.elems, tc.device) for _ in whichs]
+    fld = _field(tc, B, geom.nsd)
+    stream = torch.cuda.current_stream(tc.device).cuda_stream
+    lib = L.lib()
+    fn = lib.dn_fem_gp_eval_multi_2d_f32 if geom.nsd == 2 else lib.dn_fem_gp_eval_multi_3d_f32
+    n = len(whichs)
+    wh = (C.c_int * n)(*whichs)
+    ptrs = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    with _on_device(tc.device):
+        rc = fn(C.byref(fld), C.byref(g), n, wh, ptrs, C.c_void_p(stream))
+    L.check(rc, "dn_fem_gp_eval_multi")
+    return tuple(outs)
+
+
+class GaussPointEvalMultiFunction(torch.autograd.Function):
+    """gauss_pt_evaluation + its derivatives of ONE nodal field in one launch; backward sums the
+    cotangents of all tables in one adjoint launch."""
+
+    @staticmethod
+    def forward(ctx, t, geom, whichs):
+        ctx.geom, ctx.whichs, ctx.t_ref = geom, tuple(whichs), t
+        return _gp_multi_raw(geom, t.detach(), whichs)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):
+        geom = ctx.geom
+        used = [(w, g.contiguous()) for w, g in zip(ctx.whichs, gouts) if g is not None]
+        if not used:
+            return None, None, None
+        B = used[0][1].shape[0]
+        g = _geom_struct(geom, B)
+        dev = used[0][1].device
+        gin = _new_out((B,) + geom.spatial, dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib = L.lib()
+        fn = lib.dn_fem_gp_eval_multi_adj_2d_f32 if geom.nsd == 2 else lib.dn_fem_gp_eval_multi_adj_3d_f32
+        n = len(used)
+        wh = (C.c_int * n)(*[w for w, _ in used])
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for _, t in used])
+        with _on_device(dev):
+            rc = fn(ptrs, C.byref(g), n, wh, _ptr(gin), C.c_void_p(stream))
+        L.check(rc, "dn_fem_gp_eval_multi_adj")
+        return _like_input(gin, ctx.t_ref, geom), None, None
+
+
 # ------------------------------------------------------------------------------ public functional API
 def fem_energy(geom: Geometry, u, nu=None, f=None, f_gp=None, dirichlet: Sequence = (),
                nu_zero_mask=None, c_k=1.0, c_f=1.0, scale=1.0, reduction="mean", z_own=None,
@@ -494,3 +545,11 @@ def fem_residual(geom: Geometry, u, nu=None, f=None, dirichlet: Sequence = (), j
 
 def gp_eval(geom: Geometry, t: torch.Tensor, which: str = "N") -> torch.Tensor:
     return GaussPointEvalFunction.apply(t, geom, _WHICH[which])
+
+
+def gp_eval_multi(geom: Geometry, t: torch.Tensor, which: Sequence[str] = ("N", "dx", "dy")):
+    """(gauss_pt_evaluation(t), ..._der_x(t), ...) for the listed tables from ONE pass over `t`."""
+    whichs = tuple(_WHICH[w] for w in which)
+    if not 1 <= len(whichs) <= 4 or (geom.nsd == 2 and 3 in whichs):
+        raise ValueError(f"which={which!r}: 1..4 tables out of N, dx, dy" + (", dz" if geom.nsd == 3 else ""))
+    return GaussPointEvalMultiFunction.apply(t, geom, whichs)

@@ -216,6 +216,21 @@ int dn_fem_gp_eval_adj_2d_f32(const float* grad_out, const dn_geom* g, int which
                               void* stream);
 int dn_fem_gp_eval_adj_3d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in,
                               void* stream);
+/*
+ * Several tables in ONE pass over the input: which[w] in {0: N, 1: d/dx, 2: d/dy, 3: d/dz}, nwhich <= 4,
+ * outs[w] / grad_outs[w] dense as above.  A user loss() body that calls gauss_pt_evaluation(u),
+ * gauss_pt_evaluation_der_x(u), gauss_pt_evaluation_der_y(u) (e.g. examples/poisson/single_instance/
+ * 14_helmholtz_mms.py:50-59) streams u once; the adjoint sums the cotangents of all tables in one launch.
+ * `which`, `outs`, `grad_outs` are HOST arrays (read during the call).
+ */
+int dn_fem_gp_eval_multi_2d_f32(const dn_field* in, const dn_geom* g, int nwhich, const int* which,
+                                float* const* outs, void* stream);
+int dn_fem_gp_eval_multi_3d_f32(const dn_field* in, const dn_geom* g, int nwhich, const int* which,
+                                float* const* outs, void* stream);
+int dn_fem_gp_eval_multi_adj_2d_f32(const float* const* grad_outs, const dn_geom* g, int nwhich,
+                                    const int* which, float* grad_in, void* stream);
+int dn_fem_gp_eval_multi_adj_3d_f32(const float* const* grad_outs, const dn_geom* g, int nwhich,
+                                    const int* which, float* grad_in, void* stream);
 
 /* x[i] *= *factor_dev for i < n, skipping all memory traffic when *factor_dev == 1.0f
  * (the usual loss.backward() case).  factor_dev is a device pointer: no host sync. */

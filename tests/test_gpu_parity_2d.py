@@ -481,3 +481,33 @@ def test_errors_are_loud():
         fem.energy_loss(u, dirichlet=[(u, 0.0)] * 4)
     with pytest.raises(DiffNetFEMError):
         fem.energy_loss(u.cpu())
+
+
+@pytest.mark.parametrize("B,H,W,ngp", [(3, 70, 300, 2), (2, 33, 64, 2), (1, 9, 40, 3), (2, 17, 31, 4)])
+def test_gp_eval_marching_kernels_against_oracle(B, H, W, ngp):
+    """The marching gp-eval kernels (several x chunks / y chunks / warp seams of the adjoint) and the
+    multi-table pass: forward values and the adjoint (through autograd) against the oracle's convs in fp64."""
+    from helpers import oracle_for
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_lengths=(1.3, 0.9, 1.0), domain_size=W, ngp_1d=ngp)
+    o = oracle_for(fem)
+    g = torch.Generator().manual_seed(B * 1000 + W)
+    u = torch.randn(B, 1, H, W, generator=g)
+    ud = u.to(DEV).requires_grad_(True)
+    outs = fem.gauss_pt_evaluation_all(ud)
+    uo = u.double().requires_grad_(True)
+    refs = (o.gauss_pt_evaluation(uo), o.gauss_pt_evaluation_der_x(uo), o.gauss_pt_evaluation_der_y(uo))
+    single = (fem.gauss_pt_evaluation(ud), fem.gauss_pt_evaluation_der_x(ud), fem.gauss_pt_evaluation_der_y(ud))
+    cot = [torch.randn(r.shape, generator=g) for r in refs]
+    for a, s1, r in zip(outs, single, refs):
+        assert a.shape == r.shape
+        assert rel_l2(a.detach().cpu(), r.detach()) <= 1e-6
+        assert torch.equal(a, s1)                       # one pass == one launch per table, bit for bit
+    sum((a * c.to(DEV)).sum() for a, c in zip(outs, cot)).backward()
+    sum((r * c.double()).sum() for r, c in zip(refs, cot)).backward()
+    assert rel_l2(ud.grad.cpu(), uo.grad) <= 1e-6
+    assert float((ud.grad.cpu().double() - uo.grad).abs().max() / uo.grad.abs().max()) <= 2e-6
+    # the single-table adjoints add up to the multi-table one
+    u2 = u.to(DEV).requires_grad_(True)
+    sum((fn(u2) * c.to(DEV)).sum() for fn, c in zip((fem.gauss_pt_evaluation, fem.gauss_pt_evaluation_der_x,
+                                                     fem.gauss_pt_evaluation_der_y), cot)).backward()
+    assert rel_l2(u2.grad, ud.grad) <= 1e-6

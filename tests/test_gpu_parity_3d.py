@@ -347,3 +347,27 @@ def test_randomised_parity_sweep():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "8", "7"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "cases ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.parametrize("B,D,H,W,ngp", [(2, 9, 21, 70, 2), (1, 5, 12, 33, 2), (1, 4, 6, 9, 3)])
+def test_gp_eval_marching_kernels_against_oracle(B, D, H, W, ngp):
+    """3-D marching gp-eval kernels + the multi-table pass (N, dx, dy, dz) against the oracle's convs in fp64."""
+    from helpers import oracle_for
+    fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_lengths=(1.3, 0.9, 0.6), domain_size=W, ngp_1d=ngp)
+    o = oracle_for(fem)
+    g = torch.Generator().manual_seed(B * 1000 + W)
+    u = torch.randn(B, 1, D, H, W, generator=g)
+    ud = u.to(DEV).requires_grad_(True)
+    outs = fem.gauss_pt_evaluation_all(ud)
+    uo = u.double().requires_grad_(True)
+    refs = (o.gauss_pt_evaluation(uo), o.gauss_pt_evaluation_der_x(uo), o.gauss_pt_evaluation_der_y(uo),
+            o.gauss_pt_evaluation_der_z(uo))
+    cot = [torch.randn(r.shape, generator=g) for r in refs]
+    for a, r in zip(outs, refs):
+        assert a.shape == r.shape
+        assert rel_l2(a.detach().cpu(), r.detach()) <= 1e-6
+    assert torch.equal(outs[3], fem.gauss_pt_evaluation_der_z(ud))
+    sum((a * c.to(DEV)).sum() for a, c in zip(outs, cot)).backward()
+    sum((r * c.double()).sum() for r, c in zip(refs, cot)).backward()
+    assert rel_l2(ud.grad.cpu(), uo.grad) <= 1e-6
+    assert float((ud.grad.cpu().double() - uo.grad).abs().max() / uo.grad.abs().max()) <= 2e-6
