@@ -32,9 +32,6 @@
 namespace dn {
 
 #define DN_T3_MAXT 640      // largest CTA of any variant
-#ifndef DN_T3_ORDER
-#define DN_T3_ORDER 0
-#endif
 // Register budgets (__maxnreg__; one CTA per SM).  Registers are granted per warp in units of 1024
 // (measured: 112 registers/thread admit no more warps than 128), so the useful budgets are 96 and
 // 128: nu == 1 variants fit 96 without spills -> 640-thread CTAs (20 warps/SM, +4 % measured);
@@ -65,6 +62,7 @@ struct Link3 {
   unsigned int* tickets;        // [2] zero-initialised scratch
   int* status;                  // set to 1 if a device-side wait ran out of polls
   long long max_spins;
+  int dbg;                      // timing experiments only (DN_SLAB_DBG): 1 skip the plane copy, 2 skip the flag wait, 4 skip the loss push
 };
 
 struct P3T {
@@ -350,6 +348,38 @@ constexpr int kXParity = kXHa + kXPre + DN_T3_MAXT + 4;      // floats per parit
 constexpr int kXTrash = kXPre + DN_T3_MAXT + 2;              // slot index (within hb / ha) nobody reads
 __host__ __device__ constexpr int xbuf_bytes() { return 2 * kXParity * 4; }
 
+// Linked z-slab launch: wait (bounded) until the neighbour has released this step's halo plane, then make its
+// stores visible to the TMA unit.  Executed by the WHOLE producer warp, convergently (one broadcast load per
+// poll), as ONE opaque asm statement, at most twice per CTA.  The same loop under the elected-lane branch of the
+// producer -- as C++, as a call or as asm -- made the compiler give up the uniform datapath for the whole main
+// loop (ncu on the loopback harness: +15 % instructions -- per-thread IMAD/ISETP, BSSY/BSYNC/YIELD around every
+// refill, spills).
+__device__ __forceinline__ void wait_halo_flag(const int* flag, const int* step, long long max_spins, int* status,
+                                               int dbg) {
+  const int want = (dbg & 2) ? (int)0x80000000 : *step + 1;   // the step counter advances only in the finisher's epilogue
+  int seen;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      ".reg .s64 n;\n"
+      "mov.s64 n, 0;\n"
+      "DN_HSPIN:\n"
+      "ld.acquire.sys.global.s32 %0, [%1];\n"
+      "setp.ge.s32 P1, %0, %2;\n"
+      "@P1 bra DN_HDONE;\n"
+      "nanosleep.u32 32;\n"
+      "add.s64 n, n, 1;\n"
+      "setp.lt.s64 P1, n, %3;\n"
+      "@P1 bra DN_HSPIN;\n"
+      "DN_HDONE:\n"
+      "fence.proxy.async.global;\n"
+      "}"
+      : "=r"(seen)
+      : "l"(flag), "r"(want), "l"(max_spins)
+      : "memory");
+  if (seen < want) *status = 1;
+}
+
 // LK: linked z-slab launch (dn_slab_link) -- separate instantiations, so that the plain kernels carry none of it
 template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI, bool ISO, bool LK>
 __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_constant__ P3T p) {
@@ -372,17 +402,17 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   // neighbours' staging buffers (plain vectorised stores over NVLink), release the neighbours' flag
   // words (system scope, last CTA of a side through a ticket) and are done
   const int nputc = LK ? 2 * p.lk.nput : 0;
-  int want = 0;
   if (nputc) {
     pdl_wait();
-    want = *p.red.step + 1;
     if ((int)blockIdx.x < nputc) {
+      const int want = *p.red.step + 1;
       if (tid == 0) s_ticket = draw_start_ticket(p.red);
       const int side = (int)blockIdx.x / p.lk.nput, part = (int)blockIdx.x - side * p.lk.nput;
       if (p.lk.pdst[side]) {
         float4* dst = p.lk.pdst[side];
         const float4* src = p.lk.psrc[side];
-        for (long long i = (long long)part * NT + tid; i < p.lk.pn4; i += (long long)p.lk.nput * NT) dst[i] = src[i];
+        if (!(p.lk.dbg & 1))
+          for (long long i = (long long)part * NT + tid; i < p.lk.pn4; i += (long long)p.lk.nput * NT) dst[i] = src[i];
         __threadfence_system();
         __syncthreads();
         if (tid == 0) {
@@ -427,28 +457,17 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   // ---- producer: one elected lane of warp 0 issues one tensor copy per field per plane
   int issued = 0, ist = 0;
   auto issue_plane = [&]() {         // warp 0 only (warp-uniform)
+    const int zpl = rev ? zl - issued : zf + issued;
+    const int hs = (LK && nputc) ? ((zpl == 0 && p.lk.hflag[0]) ? 0 : ((zpl == p.nz - 1 && p.lk.hflag[1]) ? 1 : -1)) : -1;
+    if (hs >= 0) wait_halo_flag(p.lk.hflag[hs], p.red.step, p.lk.max_spins, p.lk.status, p.lk.dbg);   // the whole warp polls (one broadcast load)
     if (elect_one()) {
       uint64_t* bar = full + ist;
       float* dst = ring + ist * stage_floats;
       mbar_arrive_expect_tx(bar, (uint32_t)(NF * BX * p.BY * 4));
-      const int zpl = rev ? zl - issued : zf + issued;
-      // linked z-slab launch: the halo planes of u come from the staging buffers the neighbours fill;
-      // only the CTAs whose chunk touches them wait (bounded) for this step's flag
-      const int hs = (LK && nputc) ? ((zpl == 0 && p.lk.hflag[0]) ? 0 : ((zpl == p.nz - 1 && p.lk.hflag[1]) ? 1 : -1)) : -1;
-      if (hs >= 0) {
-        long long spins = 0;
-        int seen;
-        do {
-          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.lk.hflag[hs]) : "memory");
-          if (seen >= want) break;
-          __nanosleep(32);
-        } while (++spins < p.lk.max_spins);
-        if (seen < want) *p.lk.status = 1;
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        tma_load_4d(dst, &p.lk.tmh[hs], xs, jf, 0, 0, bar);
-      } else {
-        tma_load_4d(dst, &p.tm[0], xs, jf, zpl, b * p.bmul[0], bar);
-      }
+      const CUtensorMap* tm0 = &p.tm[0];
+      int c2 = zpl, c3 = b * p.bmul[0];
+      if (hs >= 0) { tm0 = &p.lk.tmh[hs]; c2 = 0; c3 = 0; }
+      tma_load_4d(dst, tm0, xs, jf, c2, c3, bar);
 #pragma unroll
       for (int f = 1; f < NF; ++f)
         tma_load_4d(dst + f * fstride, &p.tm[f], xs, jf, zpl, b * p.bmul[f], bar);
@@ -569,16 +588,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
   mbar_wait_u32(cbar, phase);
   F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, PA.u, PA.n, PA.f, PA.keep);
   arrive();
-#if DN_T3_ORDER == 3
-  // Half of the warps of every SM sub-partition ("late" warps) fetch a layer's upper plane at the START of the
-  // layer instead of the end of the previous one: while they run their load/mask phase (LSU, ALU) the other
-  // half runs the modal arithmetic (FMA pipe) and vice versa, instead of all four warps of a scheduler
-  // competing for the same pipe at the same time.
-  const bool late = ((warp >> 2) & 1) != 0;
-  if (!late) load_next(PB);
-#else
   load_next(PB);
-#endif
   wait_all();
   refill();                  // the stage of the first plane
 
@@ -591,24 +601,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
       if (rev) { sl = zl - 1 - (s - zf); pl = zl - (s - zf); }
     }
     Face gLo, gUp;
-#if DN_T3_ORDER == 3
-    if (late) load_next(U);
     const float2 E = F::elem_pair(k, L.u, U.u, L.n, U.n, L.f, U.f, vw, gLo, gUp);
-#elif DN_T3_ORDER == 0
-    const float2 E = F::elem_pair(k, L.u, U.u, L.n, U.n, L.f, U.f, vw, gLo, gUp);
-#else
-    // the lower faces die in the z-stage: the plane after U is fetched into their registers BEFORE the
-    // modal arithmetic, in one basic block with it, so that the load/mask/x-y-stage instructions (LSU, ALU)
-    // fill the issue slots the packed FMA-pipe instructions leave free
-    typename F::Modes M;
-    F::zstage(L.u, U.u, L.n, U.n, L.f, U.f, M);
-    const float2 keepL0 = L.keep;
-    bool early = false;
-    if constexpr (DN_T3_ORDER == 1) early = true;
-    else early = ((warp >> 2) & 1) != 0;
-    if (early && s + 2 <= zl) load_next(L);
-    const float2 E = F::elem_modes(k, M, vw, gLo, gUp);
-#endif
     const float wl = (!resid && (unsigned)(sl - elo) < (unsigned)ecnt) ? ew : 0.f;
     e32 = fmaf(wl, E.x + E.y, e32);
     Face dF;                 // plane L is complete: carry from the layer below + this layer's lower face
@@ -617,16 +610,8 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     up = gUp;
     const float2 Na01 = publish(face_to_rows(dF), po);
     arrive();              // this warp has read the stage of the U plane and published its sums of the L plane
-#if DN_T3_ORDER == 3
-    const float2 keepL = L.keep;
-    if (!late && s + 2 <= zl) load_next(L);
-#elif DN_T3_ORDER == 0
     const float2 keepL = L.keep;
     if (s + 2 <= zl) load_next(L);      // the plane after U replaces L in registers
-#else
-    const float2 keepL = keepL0;
-    if (!early && s + 2 <= zl) load_next(L);
-#endif
     wait_all();            // every warp has arrived: partial sums visible, the oldest stage is free
     refill();
     if constexpr (LK) finalize(Na01, keepL, po, pl >= z0 && pl < z1);

@@ -303,8 +303,9 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
     p.lk.status = link->status;
     p.lk.max_spins = link->max_spins > 0 ? link->max_spins : (1LL << 26);
     p.red.step = link->step;
+    p.lk.dbg = env_i3("DN_SLAB_DBG", 0);
     p.red.peer_slots = link->loss_slots;
-    p.red.rank = link->rank; p.red.world = link->world;
+    p.red.rank = link->rank; p.red.world = (p.lk.dbg & 4) ? 0 : link->world;
     if (link->loss_slots && (link->world < 1 || link->world > 32 || link->rank < 0 || link->rank >= link->world))
       return fail(DN_EINVAL, "dn_slab_link: rank %d / world %d (world <= 32)", link->rank, link->world);
   }

@@ -352,7 +352,7 @@ class ZSlabPoisson3D:
 
         def replay():
             i = state["i"]
-            if self.world > 1 and self._parity() != flip(start, i):
+            if self.world > 1 and self._peer_halo is not None and self._parity() != flip(start, i):
                 raise RuntimeError("graph replay out of step with the halo parity (an odd number of eager "
                                    "steps was mixed in); run one more eager step or re-capture")
             graphs[i].replay()

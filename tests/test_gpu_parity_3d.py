@@ -371,3 +371,19 @@ def test_gp_eval_marching_kernels_against_oracle(B, D, H, W, ngp):
     sum((r * c.double()).sum() for r, c in zip(refs, cot)).backward()
     assert rel_l2(ud.grad.cpu(), uo.grad) <= 1e-6
     assert float((ud.grad.cpu().double() - uo.grad).abs().max() / uo.grad.abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("shape", [(6, 16, 32), (10, 40, 72), (34, 64, 64)])
+def test_linked_slab_launch_loopback_one_gpu(shape):
+    """dn_fem_energy_3d_linked_f32 on ONE GPU: a middle rank linked to itself (tools/linked_loopback.py) --
+    in-launch halo put, flag wait, downward march of the lower chunk and the loss push -- against the plain
+    launch on the slab with the wrapped halo planes: owned gradient bit for bit, loss to rounding."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from linked_loopback import run
+    nl, ny, nx = shape
+    lp, gp, ll, gl, status = run(nl, ny, nx, torch.device(DEV), seed=nl)
+    assert status == 0
+    assert rel_scalar(ll, lp) < 2e-6
+    o = slice(1, nl - 1)
+    assert torch.equal(gl.reshape(nl, ny, nx)[o], gp.reshape(nl, ny, nx)[o])
