@@ -66,45 +66,87 @@ def poisson2d_parametric_batch(B: int, size: int, device, seed: int = 1234):
     return u, inputs, forcing
 
 
-def ibn2d_batch(B: int, size: int, device, seed: int = 1234):
-    """(u, inputs (B,3,H,W) = [domain, bc1, bc2], forcing) like ImageIMBack: a random star-shaped
-    object per sample (radius r(theta) = r0 (1 + sum_k a_k cos(k theta + p_k))), domain = 1 outside
-    it, bc1 = the object (u -> 1), bc2 = the four edges (u -> 0)."""
+def star_params(B: int, seed: int = 1234):
+    """(B, 11) float32 = (cx, cy, r0, a[4], phase[4]) of the synthetic star-shaped silhouettes
+    r(theta) = r0 (1 + sum_k a_k cos(k theta + p_k)), k = 2..5, and the generator (for further draws)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    y, x = torch.meshgrid(torch.linspace(-1, 1, size), torch.linspace(-1, 1, size), indexing="ij")
-    obj = torch.zeros(B, 1, size, size)
+    P = torch.zeros(B, 11)
     for b in range(B):
         c = (torch.rand(2, generator=g) - 0.5) * 0.6
-        r0 = 0.25 + 0.2 * float(torch.rand(1, generator=g))
-        th = torch.atan2(y - c[1], x - c[0])
+        P[b, 0], P[b, 1] = c[0], c[1]
+        P[b, 2] = 0.25 + 0.2 * float(torch.rand(1, generator=g))
+        for k in range(2, 6):
+            P[b, 3 + k - 2] = 0.25 * float(torch.rand(1, generator=g)) / k
+            P[b, 7 + k - 2] = 6.2831853 * float(torch.rand(1, generator=g))
+    return P, g
+
+
+def _star_raster_cpu(P: torch.Tensor, size: int) -> torch.Tensor:
+    """The silhouettes of `star_params` rasterised with torch on the CPU (the oracle legs of the bench)."""
+    y, x = torch.meshgrid(torch.linspace(-1, 1, size), torch.linspace(-1, 1, size), indexing="ij")
+    obj = torch.zeros(P.shape[0], 1, size, size)
+    for b in range(P.shape[0]):
+        cx, cy, r0 = float(P[b, 0]), float(P[b, 1]), float(P[b, 2])
+        th = torch.atan2(y - cy, x - cx)
         rad = torch.full_like(th, r0)
         for k in range(2, 6):
-            a = 0.25 * float(torch.rand(1, generator=g)) / k
-            ph = 6.2831853 * float(torch.rand(1, generator=g))
-            rad = rad + r0 * a * torch.cos(k * th + ph)
-        obj[b, 0] = (torch.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2) < rad).float()
-    domain = 1.0 - obj
-    bc2 = torch.zeros(B, 1, size, size)
-    bc2[..., 0] = 1; bc2[..., -1] = 1; bc2[:, :, 0, :] = 1; bc2[:, :, -1, :] = 1
-    inputs = torch.cat([domain, obj, bc2], 1).contiguous().to(device)
-    forcing = torch.zeros(B, 1, size, size, device=device)
+            rad = rad + r0 * float(P[b, 3 + k - 2]) * torch.cos(k * th + float(P[b, 7 + k - 2]))
+        obj[b, 0] = (torch.sqrt((x - cx) ** 2 + (y - cy) ** 2) < rad).float()
+    return obj
+
+
+def ibn2d_batch(B: int, size: int, device, seed: int = 1234):
+    """(u, inputs (B,3,H,W) = [domain, bc1, bc2], forcing) like ImageIMBack: a random star-shaped
+    object per sample, domain = 1 outside it, bc1 = the object (u -> 1), bc2 = the four edges (u -> 0).
+    On a CUDA device the three channels are rasterised by the producer kernel (dn_gen_star_inputs_f32):
+    44 bytes of parameters per sample cross PCIe instead of 12 bytes per node."""
+    P, g = star_params(B, seed)
+    if torch.device(device).type == "cuda":
+        from .datasets import star_inputs
+        inputs, forcing = star_inputs(P, size, device)
+    else:
+        obj = _star_raster_cpu(P, size)
+        bc2 = torch.zeros(B, 1, size, size)
+        bc2[..., 0] = 1; bc2[..., -1] = 1; bc2[:, :, 0, :] = 1; bc2[:, :, -1, :] = 1
+        inputs = torch.cat([1.0 - obj, obj, bc2], 1).contiguous()
+        forcing = torch.zeros(B, 1, size, size)
     u = (torch.randn(B, 1, size, size, generator=g) * 0.5 + 0.5).to(device)
     return u, inputs, forcing
 
 
-def poisson3d_parametric_batch(B: int, size: int, device, seed: int = 1234):
-    """(u, source, sink, forcing), each (B,1,D,H,W)."""
+def box_params(B: int, size: int, seed: int = 1234):
+    """(B, 19) int32 = (n, lo[3][3], hi[3][3]): 1-3 random axis-aligned boxes per sample, and the generator."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    src = torch.zeros(B, 1, size, size, size)
+    P = torch.zeros(B, 19, dtype=torch.int32)
     for b in range(B):
-        for _ in range(int(torch.randint(1, 4, (1,), generator=g))):
+        n = int(torch.randint(1, 4, (1,), generator=g))
+        P[b, 0] = n
+        for q in range(n):
             lo = torch.randint(1, size // 2, (3,), generator=g)
             ext = torch.randint(size // 8, size // 3, (3,), generator=g)
             hi = torch.minimum(lo + ext, torch.tensor(size - 1))
-            src[b, 0, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = 1
-    sink = torch.zeros(B, 1, size, size, size)
-    sink[:, :, 0] = 1; sink[:, :, -1] = 1; sink[:, :, :, 0] = 1
-    sink[:, :, :, -1] = 1; sink[..., 0] = 1; sink[..., -1] = 1
-    u = torch.rand(B, 1, size, size, size, generator=g)
-    f = torch.zeros(B, 1, size, size, size)
-    return u.to(device), src.to(device), sink.to(device), f.to(device)
+            P[b, 1 + 3 * q:4 + 3 * q] = lo.int()
+            P[b, 10 + 3 * q:13 + 3 * q] = hi.int()
+    return P, g
+
+
+def poisson3d_parametric_batch(B: int, size: int, device, seed: int = 1234):
+    """(u, source, sink, forcing), each (B,1,D,H,W): source = union of 1-3 random boxes, sink = the six faces
+    (stand-in for the SIMP topologies of IBN/poisson-3d/parametric/IBN_3D.py:76-104).  On a CUDA device the
+    masks are written by the producer kernel (dn_gen_box_masks_3d_f32)."""
+    P, g = box_params(B, size, seed)
+    if torch.device(device).type == "cuda":
+        from .datasets import box_masks_3d
+        src, sink, f = box_masks_3d(P, size, device)
+    else:
+        src = torch.zeros(B, 1, size, size, size)
+        for b in range(B):
+            for q in range(int(P[b, 0])):
+                lo, hi = P[b, 1 + 3 * q:4 + 3 * q], P[b, 10 + 3 * q:13 + 3 * q]
+                src[b, 0, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = 1
+        sink = torch.zeros(B, 1, size, size, size)
+        sink[:, :, 0] = 1; sink[:, :, -1] = 1; sink[:, :, :, 0] = 1
+        sink[:, :, :, -1] = 1; sink[..., 0] = 1; sink[..., -1] = 1
+        f = torch.zeros(B, 1, size, size, size)
+    u = torch.rand(B, 1, size, size, size, generator=g).to(device)
+    return u, src, sink, f

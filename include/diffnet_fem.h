@@ -232,6 +232,41 @@ int dn_fem_gp_eval_multi_adj_2d_f32(const float* const* grad_outs, const dn_geom
 int dn_fem_gp_eval_multi_adj_3d_f32(const float* const* grad_outs, const dn_geom* g, int nwhich,
                                     const int* which, float* grad_in, void* stream);
 
+/*
+ * Device-side producers of the path's INPUT tensors (what the reference's dataset classes build on the host with
+ * numpy and ship through a DataLoader every step).  Outputs: `inputs` dense (B, 3, [N,] H, W) fp32 =
+ * [nu or domain, bc1, bc2] and `forcing` dense (B, 1, ...) zero-filled (nullable), the layout loss() slices
+ * (examples/poisson/parametric/2_klsum_fem.py:36-38).  All pointers are device pointers unless said otherwise.
+ *
+ * dn_gen_kl_inputs_f32     KLSumStochastic (DiffNet/datasets/parametric/klsum.py:10-46) over
+ *                          generate_diffusivity_tensor (DiffNet/gen_input_calc.py:74-181): nu = exp(KL sum of `nterms`
+ *                          modes), bc1 = first column, bc2 = last column.  coeffs: (B, nterms) fp64 (the Sobol
+ *                          samples); omega: HOST array of the nterms roots for `eta` (calculate_omega_based_on_eta);
+ *                          evaluated in fp64 without fma contraction, rounded to fp32 at the end like the reference.
+ *                          nsd == 3: `inputs` is the (B, 1, N, N, N) diffusivity only (the reference has no 3-D KL
+ *                          dataset class), axes (y, x, z) as np.meshgrid orders them.  `tables`: device scratch of
+ *                          dn_gen_kl_table_bytes(nterms, size) bytes.  size % 4 == 0.
+ * dn_gen_image_inputs_f32  ImageIMBack (DiffNet/datasets/parametric/images.py:9-49): img = (B, H, W) greyscale bytes
+ *                          (PIL convert('L')); domain = 1 - (img > 0), bc1 = (img > 0), bc2 = the four edges.
+ * dn_gen_voxel_inputs_f32  VoxelIMBackRAW / load_raw (DiffNet/datasets/single_instances/voxels.py:8-61): raw = the bytes
+ *                          of <name>inouts.raw (Fortran order over numDiv = (d0, d1, d2)); inside = raw / 254.0 > 0.25;
+ *                          the block sits at `offset` (the reference hard-codes 32) in a domain_size^3 box; one sample.
+ * dn_gen_star_inputs_f32, dn_gen_box_masks_3d_f32
+ *                          synthetic immersed geometries for benchmarks / tests (no reference counterpart: stand-ins
+ *                          for its image and SIMP-topology datasets).  params: 11 floats per sample (cx, cy, r0,
+ *                          a[4], phase[4]) / 19 ints per sample (n, lo[3][3], hi[3][3]).
+ */
+size_t dn_gen_kl_table_bytes(int nterms, int size);
+int dn_gen_kl_inputs_f32(const double* coeffs, int batch, int nterms, const double* omega, double eta, int nsd,
+                         int size, void* tables, size_t table_bytes, float* inputs, float* forcing, void* stream);
+int dn_gen_image_inputs_f32(const unsigned char* img, int batch, int height, int width, float* inputs,
+                            float* forcing, void* stream);
+int dn_gen_voxel_inputs_f32(const unsigned char* raw, int d0, int d1, int d2, int domain_size, int offset,
+                            float* inputs, float* forcing, void* stream);
+int dn_gen_star_inputs_f32(const float* params, int batch, int size, float* inputs, float* forcing, void* stream);
+int dn_gen_box_masks_3d_f32(const int* params, int batch, int size, float* source, float* sink, float* forcing,
+                            void* stream);
+
 /* x[i] *= *factor_dev for i < n, skipping all memory traffic when *factor_dev == 1.0f
  * (the usual loss.backward() case).  factor_dev is a device pointer: no host sync. */
 int dn_scale_inplace_f32(float* x, size_t n, const float* factor_dev, void* stream);

@@ -106,3 +106,17 @@ def test_reference_test_scripts(golden):
     _check(g, "res2d", *_lg(lambda v: L.body_test2d_residual(fem2, v, g.t("k2")), g.t("u2")))
     fem3 = Q1Oracle(nsd=3, domain_size=8)
     _check(g, "res3d", *_lg(lambda v: L.body_test3d_residual(fem3, v, g.t("k3")), g.t("u3")))
+
+
+def test_host_kl_recipe_against_the_reference_fields():
+    """synthetic.kl_omegas / kl_diffusivity_2d (host side of the KL producer) against the reference's table and
+    fields (tests/golden/producers.npz, made from DiffNet/gen_input_calc.py by make_golden_producers.py)."""
+    import os
+    import numpy as np
+    from conftest import ROOT
+    from diffnet_b200.synthetic import kl_diffusivity_2d, kl_omegas
+    g = np.load(os.path.join(ROOT, "tests", "golden", "producers.npz"))
+    assert np.abs(kl_omegas(0.5, 6) - g["kl.omega"][:6]).max() < 1e-12
+    nu = kl_diffusivity_2d(torch.from_numpy(g["kl.coeffs"]), 16)
+    ref = torch.from_numpy(g["kl2d.inputs"][:, 0:1])
+    assert float(((nu - ref).abs() / ref).max()) < 1e-6
