@@ -570,6 +570,83 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = dof_step * world * Ke / float(te.item()) / 1e9
+    # ---- the same step with the inputs PRODUCED on the device: what crosses PCIe is u (in
+    # training it is the network's output and never leaves the device) and the 6 KL coefficients per sample
+    # (KLSumStochastic / gen_input_calc.py restated as a kernel); nu, bc1, bc2, f are written by the producer
+    e2e_prod = None
+    if name == DEFAULT:
+        try:
+            from diffnet_b200.datasets import kl_inputs
+            gco = torch.Generator(device="cpu").manual_seed(99 + rank)
+            hco = (torch.rand(B, 6, generator=gco, dtype=torch.float64) * 6.0 - 3.0).pin_memory()
+            dco = torch.empty(B, 6, dtype=torch.float64, device=dev)
+            hu, du = host[0], devbuf[0]
+
+            def prod_step():
+                du.copy_(hu, non_blocking=True)
+                dco.copy_(hco, non_blocking=True)
+                inp, frc = kl_inputs(dco, size, 2, 0.5, None, dev)
+                loss, grad = fem.energy_loss_and_grad(du, nu=inp[:, 0:1], f=frc,
+                                                      dirichlet=[(inp[:, 1:2], 1.0), (inp[:, 2:3], 0.0)])
+                return float(loss)
+            for _ in range(3):
+                prod_step()
+            barrier()
+            g0.record()
+            for _ in range(Ke):
+                prod_step()
+            g1.record()
+            torch.cuda.synchronize()
+            tp = torch.tensor([g0.elapsed_time(g1) * 1e-3], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            hb = hu.numel() * 4 + hco.numel() * 8
+            e2e_prod = {"value": dof_step * world * Ke / float(tp.item()) / 1e9, "unit": "GDOF/s",
+                        "h2d_bytes_per_step": hb, "d2h_bytes_per_step": 4, "steps": Ke,
+                        "note": "u + the KL coefficients from pinned host memory, nu/bc1/bc2/f written by the producer kernel "
+                                "(dn_gen_kl_inputs_f32), fused launch, loss.item(): the step a DiffNet training loop runs "
+                                "when its dataset lives on the device"}
+        except Exception as e:   # noqa: BLE001
+            e2e_prod = {"error": f"{type(e).__name__}: {e}"}
+    # ---- opt-in compact ingestion (same loss, same fused kernel): the two Dirichlet masks shipped as uint8
+    # (the op widens them on the device) and the all-zero source term as ONE broadcast image (stride_b = 0)
+    e2e_compact = None
+    if name == DEFAULT:
+        try:
+            hu, hin, hf = host
+            h_nu = hin[:, 0:1].contiguous().pin_memory()
+            h_m1 = (hin[:, 1:2] > 0.5).to(torch.uint8).contiguous().pin_memory()
+            h_m2 = (hin[:, 2:3] > 0.5).to(torch.uint8).contiguous().pin_memory()
+            h_f1 = hf[:1].contiguous().pin_memory()
+            hostc = [hu, h_nu, h_m1, h_m2, h_f1]
+            devc = [torch.empty_like(t, device=dev) for t in hostc]
+
+            def compact_step():
+                for h, d in zip(hostc, devc):
+                    d.copy_(h, non_blocking=True)
+                loss, grad = fem.energy_loss_and_grad(devc[0], nu=devc[1], f=devc[4],
+                                                      dirichlet=[(devc[2], 1.0), (devc[3], 0.0)])
+                return float(loss)
+            for _ in range(3):
+                compact_step()
+            barrier()
+            g0.record()
+            for _ in range(Ke):
+                compact_step()
+            g1.record()
+            torch.cuda.synchronize()
+            tc = torch.tensor([g0.elapsed_time(g1) * 1e-3], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            hb = sum(t.numel() * t.element_size() for t in hostc)
+            e2e_compact = {"value": dof_step * world * Ke / float(tc.item()) / 1e9, "unit": "GDOF/s",
+                           "h2d_bytes_per_step": hb, "d2h_bytes_per_step": 4, "steps": Ke,
+                           "h2d_gbs_per_gpu": hb * Ke / float(tc.item()) / 1e9,
+                           "note": "opt-in: Dirichlet masks as uint8 (widened on the device by the op), the zero source term as "
+                                   "one broadcast image; u and nu fp32 per sample; otherwise the e2e step"}
+            del hostc, devc
+        except Exception as e:   # noqa: BLE001
+            e2e_compact = {"error": f"{type(e).__name__}: {e}"}
     del sets, res, devbuf, host, hs
     torch.cuda.empty_cache()
     copyref = None
@@ -671,6 +748,8 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": Ke, "h2d_gbs_per_gpu": h2d * Ke / float(te.item()) / 1e9,
                     "note": "pinned host -> device copy of all input fields + fused launch + loss.item() every step; CUDA events around the steps, max over ranks"},
+            "e2e_compact_inputs": e2e_compact,
+            "e2e_device_producers": e2e_prod,
             "gpu_launches": K,
             "clocks": clocks,
             "train": train,

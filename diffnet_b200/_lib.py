@@ -81,6 +81,10 @@ PROTOTYPES = {
     "dn_fem_gp_eval_multi_3d_f32": (C.c_int, _GPM_ARGS),
     "dn_fem_gp_eval_multi_adj_2d_f32": (C.c_int, _GPMADJ_ARGS),
     "dn_fem_gp_eval_multi_adj_3d_f32": (C.c_int, _GPMADJ_ARGS),
+    "dn_fem_gp_eval_general_f32": (C.c_int, [_P(dn_field), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             _P(C.c_float), C.c_void_p, C.c_void_p]),
+    "dn_fem_gp_eval_general_adj_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 _P(C.c_float), C.c_void_p, C.c_void_p]),
     "dn_gen_kl_table_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "dn_gen_kl_inputs_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_double), C.c_double, C.c_int, C.c_int,
                                        C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -575,6 +575,28 @@ int dn_fem_gp_eval_multi_adj_3d_f32(const float* const* grad_outs, const dn_geom
   return gp_adjoint(grad_outs, g, 3, nwhich, which, grad_in, stream);
 }
 
+int dn_fem_gp_eval_general_f32(const dn_field* in, int nsd, int batch, int nx, int ny, int nz, int nbf_1d,
+                               int ngp_1d, const float* factors, float* out, void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!in || !in->ptr || !out || batch < 1) return fail(DN_EINVAL, "gp_eval_general: NULL input/output");
+  int bad = 0;
+  cudaError_t e = launch_gp_eval_general(to_field(in), batch, nsd, nx, ny, nz, nbf_1d, ngp_1d, factors, out,
+                                         (cudaStream_t)stream, &bad);
+  if (bad) return fail(DN_EINVAL, "gp_eval_general: nsd 1..3, nbf_1d 2..4, ngp_1d 1..4, (nodes - 1) %% (nbf_1d - 1) == 0");
+  return check_cuda(e, "gp_eval_general launch");
+}
+
+int dn_fem_gp_eval_general_adj_f32(const float* grad_out, int nsd, int batch, int nx, int ny, int nz, int nbf_1d,
+                                   int ngp_1d, const float* factors, float* grad_in, void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!grad_out || !grad_in || batch < 1) return fail(DN_EINVAL, "gp_eval_general_adj: NULL input/output");
+  int bad = 0;
+  cudaError_t e = launch_gp_eval_general_adj(grad_out, batch, nsd, nx, ny, nz, nbf_1d, ngp_1d, factors, grad_in,
+                                             (cudaStream_t)stream, &bad);
+  if (bad) return fail(DN_EINVAL, "gp_eval_general_adj: nsd 1..3, nbf_1d 2..4, ngp_1d 1..4, (nodes - 1) %% (nbf_1d - 1) == 0");
+  return check_cuda(e, "gp_eval_general_adj launch");
+}
+
 int dn_peer_alloc(size_t bytes, void** ptr) {
   if (int rc = device_ok(nullptr)) return rc;
   if (!ptr || bytes == 0) return fail(DN_EINVAL, "dn_peer_alloc: bad arguments");

@@ -265,3 +265,163 @@ cudaError_t launch_scale(float* x, size_t n, const float* factor_dev, cudaStream
 }
 
 }  // namespace dn
+
+// ---- general basis / rule / dimension ---------------------------------------------------------------------------
+// gauss_pt_eval for any tensor-product Lagrange basis (nbf_1d = degree + 1 nodes per direction, element stride
+// nbf_1d - 1: DiffNetFEM.py:7-18 with stride = nbf_1d - 1, :66-126 for the degree 2 / 3 bases) and for the 1-D
+// "surface" stencils of a 2-D mesh (gauss_pt_evaluation_surf, :146-147, 244-269: nsd - 1 = 1).  The caller passes
+// the 1-D factors f[d][g][b] (basis value, or derivative * 2/h for the differentiated direction): the kernels know
+// nothing about the basis.  One thread per element (forward) / node (adjoint, gather form: deterministic).
+// These are the rarely used corners of the operator family (no BASELINE config uses them): simple, not tuned.
+namespace dn {
+
+struct GpGeneral {
+  int nsd, nb, ng;            // dimensions, nodes per direction per element, Gauss points per direction
+  int n[3], nel[3];           // nodes / elements per direction, index 0 = x (innermost)
+  float f[3][4][4];           // [d][g][b]
+};
+
+__global__ void __launch_bounds__(128) k_gp_eval_general(Field in, int B, GpGeneral q, float* __restrict__ out) {
+  const int nb = q.nb, ng = q.ng, nsd = q.nsd;
+  const long long nel = (long long)q.nel[0] * q.nel[1] * q.nel[2];
+  const long long total = nel * B;
+  const int ngp = (nsd == 3) ? ng * ng * ng : (nsd == 2 ? ng * ng : ng);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ei = (int)(idx % q.nel[0]);
+    long long r = idx / q.nel[0];
+    const int ej = (int)(r % q.nel[1]);
+    r /= q.nel[1];
+    const int ek = (int)(r % q.nel[2]);
+    const int b = (int)(r / q.nel[2]);
+    const int s = nb - 1;
+    const float* base = in.p + (long long)b * in.sb + (long long)(ek * s) * in.sz + (long long)(ej * s) * in.sy + ei * s;
+    float v[4][4][4];
+    for (int kb = 0; kb < (nsd == 3 ? nb : 1); ++kb)
+      for (int jb = 0; jb < (nsd >= 2 ? nb : 1); ++jb)
+        for (int ib = 0; ib < nb; ++ib)
+          v[kb][jb][ib] = __ldg(base + (long long)kb * in.sz + (long long)jb * in.sy + ib);
+    float* o = out + (long long)b * ngp * nel + ((long long)ek * q.nel[1] + ej) * q.nel[0] + ei;
+    for (int kg = 0; kg < (nsd == 3 ? ng : 1); ++kg) {
+      float wz[4][4];
+      for (int jb = 0; jb < (nsd >= 2 ? nb : 1); ++jb)
+        for (int ib = 0; ib < nb; ++ib) {
+          float a = v[0][jb][ib];
+          if (nsd == 3) {
+            a = 0.f;
+            for (int kb = 0; kb < nb; ++kb) a += q.f[2][kg][kb] * v[kb][jb][ib];
+          }
+          wz[jb][ib] = a;
+        }
+      for (int jg = 0; jg < (nsd >= 2 ? ng : 1); ++jg) {
+        float wy[4];
+        for (int ib = 0; ib < nb; ++ib) {
+          float a = wz[0][ib];
+          if (nsd >= 2) {
+            a = 0.f;
+            for (int jb = 0; jb < nb; ++jb) a += q.f[1][jg][jb] * wz[jb][ib];
+          }
+          wy[ib] = a;
+        }
+        for (int ig = 0; ig < ng; ++ig) {
+          float a = 0.f;
+          for (int ib = 0; ib < nb; ++ib) a += q.f[0][ig][ib] * wy[ib];
+          const int G = (kg * (nsd >= 2 ? ng : 1) + jg) * ng + ig;
+          o[(long long)G * nel] = a;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_gp_eval_general_adj(const float* __restrict__ gout, int B, GpGeneral q,
+                                                             float* __restrict__ gin) {
+  const int nb = q.nb, ng = q.ng, nsd = q.nsd, s = nb - 1;
+  const long long nel = (long long)q.nel[0] * q.nel[1] * q.nel[2];
+  const long long nodes = (long long)q.n[0] * q.n[1] * q.n[2];
+  const long long total = nodes * B;
+  const int ngp = (nsd == 3) ? ng * ng * ng : (nsd == 2 ? ng * ng : ng);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c[3];
+    c[0] = (int)(idx % q.n[0]);
+    long long r = idx / q.n[0];
+    c[1] = (int)(r % q.n[1]);
+    r /= q.n[1];
+    c[2] = (int)(r % q.n[2]);
+    const int b = (int)(r / q.n[2]);
+    // per direction: the (element, local node) pairs this node belongs to (two for a node shared by neighbours)
+    int el[3][2], lb[3][2], cnt[3];
+    for (int d = 0; d < 3; ++d) {
+      cnt[d] = 0;
+      if (d >= nsd) { el[d][0] = 0; lb[d][0] = 0; cnt[d] = 1; continue; }
+      const int e = c[d] / s, l = c[d] - e * s;
+      if (e < q.nel[d]) { el[d][cnt[d]] = e; lb[d][cnt[d]] = l; ++cnt[d]; }
+      if (l == 0 && e > 0) { el[d][cnt[d]] = e - 1; lb[d][cnt[d]] = s; ++cnt[d]; }
+    }
+    const float* gb = gout + (long long)b * ngp * nel;
+    float acc = 0.f;
+    for (int pk = 0; pk < cnt[2]; ++pk)
+      for (int pj = 0; pj < cnt[1]; ++pj)
+        for (int pi = 0; pi < cnt[0]; ++pi) {
+          const float* ge = gb + ((long long)el[2][pk] * q.nel[1] + el[1][pj]) * q.nel[0] + el[0][pi];
+          for (int kg = 0; kg < (nsd == 3 ? ng : 1); ++kg) {
+            const float cz = (nsd == 3) ? q.f[2][kg][lb[2][pk]] : 1.f;
+            for (int jg = 0; jg < (nsd >= 2 ? ng : 1); ++jg) {
+              const float czy = (nsd >= 2) ? cz * q.f[1][jg][lb[1][pj]] : cz;
+              float t = 0.f;
+              for (int ig = 0; ig < ng; ++ig) {
+                const int G = (kg * (nsd >= 2 ? ng : 1) + jg) * ng + ig;
+                t += q.f[0][ig][lb[0][pi]] * __ldg(ge + (long long)G * nel);
+              }
+              acc += czy * t;
+            }
+          }
+        }
+    gin[idx] = acc;
+  }
+}
+
+static int general_setup(int nsd, int nx, int ny, int nz, int nbf_1d, int ngp_1d, const float* factors, GpGeneral* q) {
+  if (nsd < 1 || nsd > 3 || nbf_1d < 2 || nbf_1d > 4 || ngp_1d < 1 || ngp_1d > 4 || !factors) return 1;
+  const int n[3] = {nx, nsd >= 2 ? ny : 1, nsd == 3 ? nz : 1};
+  q->nsd = nsd; q->nb = nbf_1d; q->ng = ngp_1d;
+  for (int d = 0; d < 3; ++d) {
+    q->n[d] = n[d];
+    q->nel[d] = 1;
+    if (d < nsd) {
+      if (n[d] < nbf_1d || (n[d] - 1) % (nbf_1d - 1)) return 2;      // (size - 1) % degree == 0, DiffNetFEM.py:67,101
+      q->nel[d] = (n[d] - 1) / (nbf_1d - 1);
+    }
+    for (int g = 0; g < 4; ++g)
+      for (int b = 0; b < 4; ++b)
+        q->f[d][g][b] = (d < nsd && g < ngp_1d && b < nbf_1d) ? factors[((size_t)d * ngp_1d + g) * nbf_1d + b] : 0.f;
+  }
+  return 0;
+}
+
+cudaError_t launch_gp_eval_general(Field in, int B, int nsd, int nx, int ny, int nz, int nbf_1d, int ngp_1d,
+                                   const float* factors, float* out, cudaStream_t s, int* bad) {
+  GpGeneral q;
+  *bad = general_setup(nsd, nx, ny, nz, nbf_1d, ngp_1d, factors, &q);
+  if (*bad) return cudaSuccess;
+  const long long total = (long long)B * q.nel[0] * q.nel[1] * q.nel[2];
+  long long g = (total + 127) / 128;
+  const long long cap = 32LL * sm_count();
+  k_gp_eval_general<<<(int)(g > cap ? cap : (g < 1 ? 1 : g)), 128, 0, s>>>(in, B, q, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gp_eval_general_adj(const float* gout, int B, int nsd, int nx, int ny, int nz, int nbf_1d,
+                                       int ngp_1d, const float* factors, float* gin, cudaStream_t s, int* bad) {
+  GpGeneral q;
+  *bad = general_setup(nsd, nx, ny, nz, nbf_1d, ngp_1d, factors, &q);
+  if (*bad) return cudaSuccess;
+  const long long total = (long long)B * q.n[0] * q.n[1] * q.n[2];
+  long long g = (total + 127) / 128;
+  const long long cap = 32LL * sm_count();
+  k_gp_eval_general_adj<<<(int)(g > cap ? cap : (g < 1 ? 1 : g)), 128, 0, s>>>(gout, B, q, gin);
+  return cudaGetLastError();
+}
+
+}  // namespace dn

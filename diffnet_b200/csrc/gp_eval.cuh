@@ -29,6 +29,11 @@ struct GpMultiAdj {
 cudaError_t launch_gp_eval(Field in, int B, int nx, int ny, int nz, int nsd, const GpMulti& m, cudaStream_t s);
 cudaError_t launch_gp_eval_adj(int B, int nx, int ny, int nz, int nsd, const GpMultiAdj& m, float* gin,
                                cudaStream_t s);
+// any tensor-product Lagrange basis / rule / 1..3 dimensions; factors = host [nsd][ngp_1d][nbf_1d]; *bad != 0: rejected
+cudaError_t launch_gp_eval_general(Field in, int B, int nsd, int nx, int ny, int nz, int nbf_1d, int ngp_1d,
+                                   const float* factors, float* out, cudaStream_t s, int* bad);
+cudaError_t launch_gp_eval_general_adj(const float* gout, int B, int nsd, int nx, int ny, int nz, int nbf_1d,
+                                       int ngp_1d, const float* factors, float* gin, cudaStream_t s, int* bad);
 cudaError_t launch_scale(float* x, size_t n, const float* factor_dev, cudaStream_t s);
 
 }  // namespace dn

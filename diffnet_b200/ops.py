@@ -14,6 +14,7 @@ import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -522,6 +523,65 @@ class GaussPointEvalMultiFunction(torch.autograd.Function):
             rc = fn(ptrs, C.byref(g), n, wh, _ptr(gin), C.c_void_p(stream))
         L.check(rc, "dn_fem_gp_eval_multi_adj")
         return _like_input(gin, ctx.t_ref, geom), None, None
+
+
+class GaussPointEvalGeneralFunction(torch.autograd.Function):
+    """gauss_pt_eval for any tensor-product Lagrange basis / rule in 1-3 dimensions
+    (dn_fem_gp_eval_general_f32): the degree 2 / 3 bases and the 1-D surface stencils."""
+
+    @staticmethod
+    def forward(ctx, t, nsd, nb, ng, factors):
+        _require_cuda(t, "tensor")
+        if t.dtype != torch.float32:
+            raise L.DiffNetFEMError(f"tensor must be float32 (got {t.dtype})")
+        tc = t.detach()
+        if tc.dim() == nsd + 2:
+            if tc.shape[1] != 1:
+                raise L.DiffNetFEMError(f"expected one channel, got shape {tuple(tc.shape)}")
+            tc = tc[:, 0]
+        elif tc.dim() == nsd:
+            tc = tc.unsqueeze(0)
+        elif tc.dim() != nsd + 1:
+            raise L.DiffNetFEMError(f"bad shape {tuple(tc.shape)} for a {nsd}-D nodal field")
+        if tc.stride(-1) != 1:
+            tc = tc.contiguous()
+        B = tc.shape[0]
+        sp = tuple(tc.shape[1:])                                   # ([nz, ny,] nx)
+        if any((n - 1) % (nb - 1) for n in sp):
+            raise L.DiffNetFEMError(f"nodes {sp}: (n - 1) must be a multiple of the basis degree {nb - 1}")
+        nel = tuple((n - 1) // (nb - 1) for n in sp)
+        n3 = (1,) * (3 - nsd) + sp                                 # (nz, ny, nx)
+        fac = np.ascontiguousarray(np.asarray(factors, dtype=np.float32).reshape(nsd, ng, nb))
+        out = _new_out((B, ng ** nsd) + nel, tc.device)
+        fld = L.dn_field(tc.data_ptr(), tc.stride(0), tc.stride(1) if nsd == 3 else 0,
+                         tc.stride(nsd - 1) if nsd >= 2 else 0)
+        stream = torch.cuda.current_stream(tc.device).cuda_stream
+        with _on_device(tc.device):
+            rc = L.lib().dn_fem_gp_eval_general_f32(C.byref(fld), nsd, B, n3[2], n3[1], n3[0], nb, ng,
+                                                    fac.ctypes.data_as(C.POINTER(C.c_float)), _ptr(out), C.c_void_p(stream))
+        L.check(rc, "dn_fem_gp_eval_general_f32")
+        ctx.meta = (nsd, nb, ng, fac, n3, B, sp)
+        ctx.t_shape = tuple(t.shape)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        nsd, nb, ng, fac, n3, B, sp = ctx.meta
+        gout = gout.contiguous()
+        gin = _new_out((B,) + sp, gout.device)
+        stream = torch.cuda.current_stream(gout.device).cuda_stream
+        with _on_device(gout.device):
+            rc = L.lib().dn_fem_gp_eval_general_adj_f32(_ptr(gout), nsd, B, n3[2], n3[1], n3[0], nb, ng,
+                                                        fac.ctypes.data_as(C.POINTER(C.c_float)), _ptr(gin), C.c_void_p(stream))
+        L.check(rc, "dn_fem_gp_eval_general_adj_f32")
+        return gin.reshape(ctx.t_shape), None, None, None, None
+
+
+def gp_eval_general(t: torch.Tensor, nsd: int, nbf_1d: int, ngp_1d: int, factors) -> torch.Tensor:
+    """``factors[d][g][b]``, d = 0 (x) .. nsd-1: the 1-D basis value (or derivative * 2/h) of local node b at
+    Gauss point g.  Returns (B, ngp_1d^nsd, elements...)."""
+    return GaussPointEvalGeneralFunction.apply(t, nsd, nbf_1d, ngp_1d, factors)
 
 
 # ------------------------------------------------------------------------------ public functional API

@@ -14,6 +14,7 @@ Not on the hot path.  Recipes restated from the reference:
 """
 from __future__ import annotations
 
+import functools
 import math
 
 import numpy as np
@@ -21,7 +22,12 @@ import torch
 
 
 def kl_omegas(eta: float, n: int = 6) -> np.ndarray:
-    """First n positive roots of (eta^2 w^2 - 1) sin(w) - 2 eta w cos(w) = 0."""
+    """First n positive roots of (eta^2 w^2 - 1) sin(w) - 2 eta w cos(w) = 0 (cached per (eta, n))."""
+    return np.array(_kl_omegas(float(eta), int(n)))
+
+
+@functools.lru_cache(maxsize=32)
+def _kl_omegas(eta: float, n: int):
     g = lambda w: (eta * eta * w * w - 1.0) * math.sin(w) - 2.0 * eta * w * math.cos(w)
     roots, w, step = [], 1e-6, 1e-3
     prev = g(w)
@@ -38,7 +44,7 @@ def kl_omegas(eta: float, n: int = 6) -> np.ndarray:
                     a = m
             roots.append(0.5 * (a + b))
         w, prev = w2, cur
-    return np.array(roots)
+    return tuple(roots)
 
 
 def kl_diffusivity_2d(coeffs: torch.Tensor, size: int, eta: float = 0.5) -> torch.Tensor:

@@ -233,6 +233,20 @@ int dn_fem_gp_eval_multi_adj_3d_f32(const float* const* grad_outs, const dn_geom
                                     const int* which, float* grad_in, void* stream);
 
 /*
+ * gauss_pt_eval for ANY tensor-product Lagrange basis and rule, in 1, 2 or 3 dimensions: the quadratic / cubic bases
+ * (fem_basis_deg 2 / 3: nbf_1d = 3 / 4 nodes per direction, elements every nbf_1d - 1 nodes -- DiffNetFEM.py:7-18 with
+ * stride = nbf_1d - 1, :66-126) and the 1-D surface stencils of a 2-D mesh (gauss_pt_evaluation_surf, :146-147,
+ * 244-269: nsd = 1).  factors = HOST array [nsd][ngp_1d][nbf_1d] of the 1-D factors per direction (0 = x): basis value
+ * at the Gauss point, or derivative * 2/h for the differentiated direction.  in: nodes (B, [nz, ny,] nx) through its
+ * strides; out dense (B, ngp_1d^nsd, elements...), G = (kg ngp + jg) ngp + ig; grad_in dense nodes (overwritten).
+ * (nodes - 1) % (nbf_1d - 1) == 0 per direction.  Q1 meshes in 2-D / 3-D take the tuned dn_fem_gp_eval_* above.
+ */
+int dn_fem_gp_eval_general_f32(const dn_field* in, int nsd, int batch, int nx, int ny, int nz, int nbf_1d,
+                               int ngp_1d, const float* factors, float* out, void* stream);
+int dn_fem_gp_eval_general_adj_f32(const float* grad_out, int nsd, int batch, int nx, int ny, int nz, int nbf_1d,
+                                   int ngp_1d, const float* factors, float* grad_in, void* stream);
+
+/*
  * Device-side producers of the path's INPUT tensors (what the reference's dataset classes build on the host with
  * numpy and ship through a DataLoader every step).  Outputs: `inputs` dense (B, 3, [N,] H, W) fp32 =
  * [nu or domain, bc1, bc2] and `forcing` dense (B, 1, ...) zero-filled (nullable), the layout loss() slices

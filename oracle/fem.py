@@ -173,3 +173,77 @@ class Q1Oracle:
 
     def gauss_pt_evaluation_der_z(self, t):
         return gp_eval(t, self.dN_z_gp, self.nsd)
+
+
+# ------------------------------------------------------------------ degree 2 / 3 and the surface stencils
+def lagrange_basis_1d(deg: int):
+    """(values(x), derivatives(x)) of the equispaced Lagrange basis of degree 1..3 on [-1,1],
+    DiffNetFEM.py:58-59 (deg 1), :71-80 (deg 2), :105-117 (deg 3).  Upstream writes ``dtype=np.float`` in the
+    deg 2/3 lambdas, which numpy >= 1.24 rejects; the polynomials themselves are restated unchanged."""
+    if deg == 1:
+        return (lambda x: np.array([0.5 * (1. - x), 0.5 * (1. + x)]),
+                lambda x: np.array([0.5 * (0. - 1.), 0.5 * (0. + 1.)]))
+    if deg == 2:
+        return (lambda x: np.array([0.5 * x * (x - 1.), (1. - x ** 2), 0.5 * x * (x + 1.)], dtype=float),
+                lambda x: np.array([0.5 * (2. * x - 1.), (- 2. * x), 0.5 * (2. * x + 1.)], dtype=float))
+    if deg == 3:
+        return (lambda x: np.array([(-9. / 16.) * (x ** 3 - x ** 2 - (1. / 9.) * x + (1. / 9.)),
+                                    (27. / 16.) * (x ** 3 - (1. / 3.) * x ** 2 - x + (1. / 3.)),
+                                    (-27. / 16.) * (x ** 3 + (1. / 3.) * x ** 2 - x - (1. / 3.)),
+                                    (9. / 16.) * (x ** 3 + x ** 2 - (1. / 9.) * x - (1. / 9.))], dtype=float),
+                lambda x: np.array([(-9. / 16.) * (3 * x ** 2 - 2 * x - (1. / 9.)),
+                                    (27. / 16.) * (3 * x ** 2 - (2. / 3.) * x - 1),
+                                    (-27. / 16.) * (3 * x ** 2 + (2. / 3.) * x - 1),
+                                    (9. / 16.) * (3 * x ** 2 + 2 * x - (1. / 9.))], dtype=float))
+    raise ValueError("fem_basis_deg must be 1, 2 or 3")
+
+
+class LagrangeOracle:
+    """gauss_pt_evaluation{,_der_x,_der_y,_der_z,_surf} for fem_basis_deg 1..3: one strided convolution per Gauss
+    point (stride = nbf_1d - 1, DiffNetFEM.py:143-156 with :7-18), stencils built as :197-215 / :405-453 do, surface
+    stencils as :244-269.  sizes / lengths are (X, Y[, Z])."""
+
+    def __init__(self, nsd, sizes, lengths, fem_basis_deg=1, ngp_1d=2, dtype=torch.float64):
+        self.nsd, self.deg = nsd, fem_basis_deg
+        self.ngp_1d = max(int(ngp_1d), 2 if fem_basis_deg == 1 else 3)           # :27-38
+        self.nbf_1d = nb = fem_basis_deg + 1
+        self.gpx_1d, self.gpw_1d = gauss_rule(self.ngp_1d)
+        nel = [int((s - 1) / fem_basis_deg) for s in sizes[:nsd]]                # :42-46
+        hs = [l / n for l, n in zip(lengths[:nsd], nel)]
+        bf, der = lagrange_basis_1d(fem_basis_deg)
+        B = [bf(x) for x in self.gpx_1d]
+        D = [der(x) for x in self.gpx_1d]
+        ng = self.ngp_1d
+        self.tables = {k: [] for k in ("N", "dx", "dy", "dz")[:nsd + 1]}
+        for gp in np.ndindex(*(ng,) * nsd):                                      # ([kg,] jg, ig)
+            g = gp[::-1]                                                         # (ig, jg[, kg])
+            for w, key in enumerate(self.tables):
+                fac = [D[g[d]] if w == d + 1 else B[g[d]] for d in range(nsd)]
+                tab = fac[0]
+                for d in range(1, nsd):
+                    tab = tab * fac[d].reshape((nb,) + (1,) * d)                 # x * y [* z], like the reference
+                if w > 0:
+                    tab = tab * (2 / hs[w - 1])
+                t32 = torch.zeros(tab.shape)
+                t32.copy_(torch.from_numpy(np.ascontiguousarray(tab)))           # f64 -> f32 rounding on store
+                self.tables[key].append(t32[None, None].to(dtype))
+        self.surf = [torch.tensor(B[g], dtype=torch.float32)[None, None].to(dtype) for g in range(ng)]
+
+    def _eval(self, t, key):
+        conv = {2: F.conv2d, 3: F.conv3d}[self.nsd]
+        return torch.cat([conv(t, w, stride=self.nbf_1d - 1) for w in self.tables[key]], dim=1)
+
+    def gauss_pt_evaluation(self, t):
+        return self._eval(t, "N")
+
+    def gauss_pt_evaluation_der_x(self, t):
+        return self._eval(t, "dx")
+
+    def gauss_pt_evaluation_der_y(self, t):
+        return self._eval(t, "dy")
+
+    def gauss_pt_evaluation_der_z(self, t):
+        return self._eval(t, "dz")
+
+    def gauss_pt_evaluation_surf(self, t):
+        return torch.cat([F.conv1d(t, w, stride=self.nbf_1d - 1) for w in self.surf], dim=1)
