@@ -206,7 +206,8 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   if (path && !strcmp(path, "tile")) return DN_OK;
   if (!vec4 || fgp.p || ((uintptr_t)grad % 16 != 0)) return DN_OK;
   const bool iso = nu.p && k.kx == k.ky && k.kx == k.kz && k.kx != 0.f && env_i3("DN_T3_ISO", 1);
-  const int NU = nu.p ? (iso ? 2 : 1) : 0, F = f.p ? 1 : 0, NMK = numask.p ? 1 : 0;
+  const bool iso1 = !nu.p && k.kx == k.ky && k.kx == k.kz && env_i3("DN_T3_ISO", 1);
+  const int NU = nu.p ? (iso ? 2 : 1) : (iso1 ? 3 : 0), F = f.p ? 1 : 0, NMK = numask.p ? 1 : 0;
   int MKx = MK;
   if (!mask_input) {                     // operator apply: only the plain-mask, no-source variants exist
     if (MK == 0) MKx = 0;
@@ -221,13 +222,13 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   memset(&p, 0, sizeof(p));
   int nf = 0;
   fl[nf++] = u;
-  if (NU) fl[nf++] = nu;
+  if (nu.p) fl[nf++] = nu;
   if (F) fl[nf++] = f;
   if (NMK) fl[nf++] = numask;
   for (int i = 0; i < nmasks; ++i) { fl[nf++] = mk[i].m; p.mval[i] = mk[i].v; }
   if (MK == 4) fl[nf++] = mk[0].vf;
   const long long min_grid = (link && link->halo_plane[0] && env_i3("DN_SLAB_WAVES", 0)) ? (long long)(1.9 * sms) : 0;
-  Plan3T pl = plan3t(g, nf, sms, occ, DN_T3_MAXT_OF(NU), min_grid);
+  Plan3T pl = plan3t(g, nf, sms, occ, DN_T3_MAXT_OF(nu.p != nullptr), min_grid);
   if (!pl.ok) { cudaGetLastError(); return DN_OK; }
   if (pl.grid > 0x7fffffffLL) return DN_OK;
   int nput = 0;
@@ -260,6 +261,7 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   p.k3.nkfttt = pr(-k.kf * t * t * t);
   p.k3.c0x = pr(8.f * k.kx); p.k3.c0y = pr(8.f * k.ky); p.k3.c0z = pr(8.f * k.kz);
   p.k3.kscale = 1.f;
+  p.k3.c0_2t = pr(2.f * 8.f * k.kx * t); p.k3.c0_3tt = pr(3.f * 8.f * k.kx * t * t);
   if (iso) {
     // isotropic spacing: k moves out of the element (see K3); the source constants absorb 1/k
     p.k3.kscale = k.kx;
