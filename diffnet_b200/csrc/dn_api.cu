@@ -195,7 +195,7 @@ static Plan2D plan2d(const dn_geom* g, bool vec4, int sms) {
 static size_t ws_bytes_for_grid(long long grid) { return 64 + 8 * (size_t)grid; }
 
 // ---- streaming (bulk-async) 2-D path -------------------------------------------------------
-struct Plan2T { int ok, threads, S, R, nchunks, nf; long long grid; size_t smem; };
+struct Plan2T { int ok, threads, S, R, nchunks, nf, bal_q, bal_rem; long long grid; size_t smem; };
 
 static size_t smem_2t(int S, int nf, int nx, int threads) {
   return (size_t)S * nf * 2 * nx * 4 + 16 + (size_t)S * 8 + 4 * (size_t)(threads / 32) * 4;
@@ -236,12 +236,26 @@ static Plan2T plan2t(const dn_geom* g, int nf, int sms, occ2t_fn occ) {
   // 256-row chunks (fewer, longer-lived CTAs expose every ring refill)
   const int Rmax = env_int("DN_T2_RMAX", 32);
   if (R > Rmax && Rmax >= Rmin) R = Rmax;
-  R = env_int("DN_T2_R", R);
+  const int Rforced = env_int("DN_T2_R", 0);
+  if (Rforced > 0) R = Rforced;
   if (R < 4) R = 4;
   if (R > g->ny) R = g->ny;
   pl.R = R;
   pl.nchunks = (g->ny + R - 1) / R;
   pl.grid = (long long)g->batch * pl.nchunks;
+  // One wave, balanced: uniform R-row chunks leave a short last chunk per image (256 rows / 15 -> 17 chunks + a
+  // 1-row chunk) and fewer CTAs than slots (1152 of 1184: 32 SMs run 7 CTAs, the rest 8 -- the kernel ends with the
+  // busiest SM).  Instead every slot gets one CTA: the first `rem` images are cut into q + 1 chunks, the others into
+  // q, each image into equal parts (rows differ by at most one).
+  if (Rforced <= 0 && env_int("DN_T2_BALANCE", 1) && pl.grid <= slots && slots <= (long long)g->batch * (g->ny / Rmin)) {
+    const long long q = slots / g->batch, rem = slots % g->batch;
+    if (q >= 1 && g->ny / (q + 1) >= Rmin && (g->ny + q - 1) / q <= Rmax) {
+      pl.bal_q = (int)q; pl.bal_rem = (int)rem;
+      pl.grid = slots;
+      pl.nchunks = (int)q + (rem ? 1 : 0);
+      pl.R = (int)((g->ny + q - 1) / q);
+    }
+  }
   pl.ok = 1;
   return pl;
 }
@@ -283,6 +297,7 @@ static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, int m
   p.nf = nf;
   p.B = g->batch; p.nx = g->nx; p.ny = g->ny;
   p.R = pl.R; p.nchunks = pl.nchunks; p.S = pl.S;
+  p.bal_q = pl.bal_q; p.bal_rem = pl.bal_rem;
   const float kx = c.k.kx, ky = c.k.ky, kf = c.k.kf, t = c.k.t;
   p.k2.kx = make_float2(kx, kx); p.k2.ky = make_float2(ky, ky); p.k2.t = make_float2(t, t);
   p.k2.kxt = make_float2(kx * t, kx * t); p.k2.kyt = make_float2(ky * t, ky * t);
@@ -369,7 +384,7 @@ int dn_debug_plan(const dn_geom* g, int nfields, int has_nu, int64_t out[16]) {
     out[0] = pl.ok;
     if (pl.ok) {
       out[1] = pl.threads; out[2] = pl.grid; out[3] = (int64_t)pl.smem; out[4] = pl.S;
-      out[5] = pl.R; out[6] = pl.nchunks;
+      out[5] = pl.R; out[6] = pl.nchunks; out[7] = pl.bal_q; out[8] = pl.bal_rem;
     }
     return DN_OK;
   }

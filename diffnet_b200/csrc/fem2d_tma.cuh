@@ -41,6 +41,7 @@ struct P2T {
   int nf;
   int B, nx, ny;
   int R, nchunks, S;
+  int bal_q, bal_rem;       // bal_q > 0: balanced one-wave split -- images [0, bal_rem) have bal_q + 1 equal chunks, the rest bal_q
   K2 k2;                    // packed (pair-replicated) constants, read straight from the constant bank
   float* grad;              // dense (B, ny, nx); nullable (forward only)
   Reduce red;
@@ -343,8 +344,20 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_floats + 4);  // [S]
   float* seam = reinterpret_cast<float*>(full + S);                                   // [2 parities][2 rows][nw]
 
-  const int b = blockIdx.x / p.nchunks, ch = blockIdx.x - b * p.nchunks;
-  const int r_begin = ch * p.R, r_end = min(p.ny, r_begin + p.R);
+  int b, r_begin, r_end;
+  if (p.bal_q > 0) {
+    const int c = (int)blockIdx.x, hi = p.bal_rem * (p.bal_q + 1);
+    int n, ch;
+    if (c < hi) { n = p.bal_q + 1; b = c / n; ch = c - b * n; }
+    else { n = p.bal_q; const int c2 = c - hi; b = c2 / n; ch = c2 - b * n; b += p.bal_rem; }
+    r_begin = (int)((long long)ch * p.ny / n);
+    r_end = (int)((long long)(ch + 1) * p.ny / n);
+  } else {
+    b = blockIdx.x / p.nchunks;
+    const int ch = blockIdx.x - b * p.nchunks;
+    r_begin = ch * p.R;
+    r_end = min(p.ny, r_begin + p.R);
+  }
   const int j_first = max(r_begin - 1, 0), j_last = min(r_end, p.ny - 1);
   const int nrows = j_last - j_first + 1;          // node rows streamed: >= 2
   const int nst = (nrows + 1) >> 1;                // stages streamed (the last may hold one row)

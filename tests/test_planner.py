@@ -23,10 +23,17 @@ def test_2d_plans_are_launchable(B):
         for nf in (1, 3, 5, 7):
             p, ws = plan(2, B, nx, ny, 1, nf)
             assert p[0] == 1, (B, nx, ny)
-            threads, grid, smem, S, R, nch = p[1:7]
+            threads, grid, smem, S, R, nch, bal_q, bal_rem = p[1:9]
             assert threads % 32 == 0 and nx // 4 <= threads <= 512
             assert smem <= 226 * 1024 and S >= 2
-            assert R >= 1 and nch * R >= ny and (nch - 1) * R < ny and grid == B * nch
+            if bal_q:       # balanced one-wave split: bal_rem images in bal_q + 1 equal parts, the rest in bal_q
+                assert 0 <= bal_rem < B and grid == bal_rem * (bal_q + 1) + (B - bal_rem) * bal_q == 148 * 8
+                for n in {bal_q, bal_q + 1 if bal_rem else bal_q}:
+                    cuts = [ch * ny // n for ch in range(n + 1)]
+                    assert cuts[0] == 0 and cuts[-1] == ny and min(b - a for a, b in zip(cuts, cuts[1:])) >= 8
+                    assert max(b - a for a, b in zip(cuts, cuts[1:])) <= R <= 32
+            else:
+                assert R >= 1 and nch * R >= ny and (nch - 1) * R < ny and grid == B * nch
             assert 64 + 8 * grid <= ws
     assert plan(2, B, 2052, 64, 1)[0][0] == 0        # wider than a CTA: the general kernel takes it
     assert plan(2, B, 130, 64, 1)[0][0] == 0         # nx % 4 != 0

@@ -1,5 +1,5 @@
-for lib in variants/lib_prev.so diffnet_b200/lib/libdiffnet_fem.so; do
-  echo "=== lib $lib"
-  DIFFNET_FEM_LIB=$PWD/$lib python tools/sweep.py --graph --n 30 poisson3d_param_64_b16 poisson3d_256_b1 2>&1 | grep -v Warning
+for cfg in "DN_T2_BALANCE=0" ""; do
+  echo "=== $cfg"
+  env $cfg python tools/sweep.py --graph --n 50 poisson2d_param_256_b64 poisson2d_512_b16 ibn2d_512_b16 poisson2d_param_256_b16 2>&1 | grep -v Warning
 done
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -m pytest tests/test_gpu_parity_2d.py -m gpu -x -q 2>&1 | tail -2
