@@ -359,8 +359,16 @@ int dn_device_check(void) { return device_ok(nullptr); }
 
 size_t dn_fem_workspace_bytes(const dn_geom* g) {
   if (!g) return 0;
-  // upper bound over both lane widths and any env override; grids are <= items
+  // upper bound over both lane widths and any env override; grids are <= items.  Host-only query: the SM count of
+  // the current device when there is one, else the B200's 148
   int sms = 148;
+  {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      sms = n;
+    cudaGetLastError();
+  }
   long long worst = 0;
   if (g->nsd == 2) {
     for (int v = 0; v < 2; ++v) {

@@ -1,0 +1,45 @@
+"""tools/gp_probe.py [n] -- the un-fused gauss_pt_evaluation forward / multi-table / adjoint launches at the two
+BASELINE batch shapes (256^2 x 64, 64^3 x 16), timed with CUDA events; the command ncu profiles for gp_eval."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from diffnet_b200 import DiffNet2DFEM, DiffNet3DFEM, ops
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+dev = "cuda:0"
+peak = 6455.6
+for fem, shape in ((DiffNet2DFEM(None, domain_size=256), (64, 1, 256, 256)), (DiffNet3DFEM(None, domain_size=64), (16, 1, 64, 64, 64))):
+    us = [torch.randn(shape, device=dev) for _ in range(4)]
+    ngp = fem.ngp_total
+    nel = 1
+    for s in fem.geometry.elems:
+        nel *= s
+    nodes = us[0].numel()
+    outs = ops._gp_raw(fem.geometry, us[0], 0)
+    cots = [torch.randn_like(outs) for _ in range(2)]
+    which = (0, 1, 2) if fem.nsd == 2 else (0, 1, 2, 3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, nbytes, label):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us_ = e0.elapsed_time(e1) / n * 1e3
+        print(f"{fem.nsd}-D {label:28s} {us_:8.1f} us  {nbytes / us_ / 1e3:7.0f} GB/s  {nbytes / us_ / 1e3 / peak:.3f} of peak", flush=True)
+
+    u_req = [u.clone().requires_grad_(True) for u in us]
+    timed(lambda i: ops._gp_raw(fem.geometry, us[i % 4], 0), 4 * nodes + 4 * shape[0] * ngp * nel, "forward, one table")
+    timed(lambda i: ops._gp_multi_raw(fem.geometry, us[i % 4], which), 4 * nodes + 4 * len(which) * shape[0] * ngp * nel, f"forward, {len(which)} tables, one pass")
+
+    def adj(i):
+        out = ops.gp_eval(fem.geometry, u_req[i % 4], "N")
+        out.backward(cots[i % 2])
+    timed(adj, 2 * (4 * nodes + 4 * shape[0] * ngp * nel), "forward + adjoint (autograd)")
