@@ -1,5 +1,23 @@
-for cfg in "DN_T2_BALANCE=0" ""; do
-  echo "=== $cfg"
-  env $cfg python tools/sweep.py --graph --n 50 poisson2d_param_256_b64 poisson2d_512_b16 ibn2d_512_b16 poisson2d_param_256_b16 2>&1 | grep -v Warning
-done
-python -m pytest tests/test_gpu_parity_2d.py -m gpu -x -q 2>&1 | tail -2
+python - <<'PY'
+import torch, time
+from diffnet_b200 import DiffNet2DFEM, ops
+dev="cuda:0"
+fem=DiffNet2DFEM(None, domain_size=256)
+u=torch.randn(64,1,256,256,device=dev,requires_grad=True)
+out=ops.gp_eval(fem.geometry,u,"N")
+cot=torch.randn_like(out)
+for i in range(3):
+    out=ops.gp_eval(fem.geometry,u,"N"); out.backward(cot)
+torch.cuda.synchronize()
+e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+for i in range(3):
+    out=ops.gp_eval(fem.geometry,u,"N")
+    torch.cuda.synchronize(); t=time.time(); e0.record()
+    out.backward(cot)
+    e1.record(); torch.cuda.synchronize()
+    print("backward: device %.1f us  wall %.1f us" % (e0.elapsed_time(e1)*1e3, (time.time()-t)*1e6))
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    out=ops.gp_eval(fem.geometry,u,"N"); out.backward(cot); torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=8))
+PY
