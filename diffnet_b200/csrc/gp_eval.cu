@@ -35,22 +35,28 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval(Field in, int nx, int ny
   const float* base = in.p + (long long)b * in.sb + (NSD == 3 ? (long long)k * in.sz : 0) + (long long)j0 * in.sy + i;
   const long long obase = (long long)b * NGP * nel + ((long long)k * nely + j0) * nelx + i;
 
+  // node rows j (jb = 0) and j + 1 (jb = 1) of the element row in flight, plus row j + 2 prefetched one
+  // iteration ahead: its loads are issued before the arithmetic and the stores of element row j
   float v[NZ][2][2];       // [kb][jb][ib]
+  float nx2[NZ][2];        // row j + 2
 #pragma unroll
   for (int kb = 0; kb < NZ; ++kb) {
     const float* q = base + (long long)kb * in.sz;
-    v[kb][1][0] = __ldg(q);
-    v[kb][1][1] = __ldg(q + 1);
+    v[kb][0][0] = __ldg(q);
+    v[kb][0][1] = __ldg(q + 1);
+    v[kb][1][0] = __ldg(q + in.sy);
+    v[kb][1][1] = __ldg(q + in.sy + 1);
   }
+  base += 2 * in.sy;
   for (int j = j0; j < j1; ++j) {
-    base += in.sy;
+    const bool more = (j + 2 <= nely);                    // node row j + 2 exists (it is row nely at most)
 #pragma unroll
     for (int kb = 0; kb < NZ; ++kb) {
       const float* q = base + (long long)kb * in.sz;
-      v[kb][0][0] = v[kb][1][0]; v[kb][0][1] = v[kb][1][1];
-      v[kb][1][0] = __ldg(q);
-      v[kb][1][1] = __ldg(q + 1);
+      nx2[kb][0] = more ? __ldg(q) : 0.f;
+      nx2[kb][1] = more ? __ldg(q + 1) : 0.f;
     }
+    base += in.sy;
     const long long orow = obase + (long long)(j - j0) * nelx;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -76,6 +82,11 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval(Field in, int nx, int ny
           }
         }
       }
+    }
+#pragma unroll
+    for (int kb = 0; kb < NZ; ++kb) {
+      v[kb][0][0] = v[kb][1][0]; v[kb][0][1] = v[kb][1][1];
+      v[kb][1][0] = nx2[kb][0];  v[kb][1][1] = nx2[kb][1];
     }
   }
 }
@@ -183,11 +194,13 @@ static int sm_count() {
 // Rows per chunk: long enough that the re-read halo row is cheap (1/RY), short enough that the grid has
 // several CTAs per SM slot.
 static int rows_per_chunk(long long columns_ctas, int rows) {
-  const long long want = 8LL * sm_count();                 // CTAs in the grid
+  // these kernels are latency-bound at low occupancy (ncu: 0.54 waves, long_scoreboard 9 per issue with
+  // 8 CTAs per SM in the grid): fill the machine -- 16 resident 128-thread CTAs per SM, two waves of them
+  const long long want = 32LL * sm_count();                // CTAs in the grid
   long long chunks = (want + columns_ctas - 1) / columns_ctas;
   if (chunks < 1) chunks = 1;
   int ry = (int)((rows + chunks - 1) / chunks);
-  if (ry < 8) ry = 8;
+  if (ry < 4) ry = 4;
   if (ry > rows) ry = rows;
   return ry < 1 ? 1 : ry;
 }

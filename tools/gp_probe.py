@@ -44,3 +44,27 @@ for fem, shape in ((DiffNet2DFEM(None, domain_size=256), (64, 1, 256, 256)), (Di
     def adj(i):
         torch.autograd.grad(held[i % 2], u_req[i % 2], cots[i % 2], retain_graph=True)
     timed(adj, 4 * nodes + 4 * shape[0] * ngp * nel, "adjoint (autograd.grad)")
+
+
+# device-side kernel durations (the eager numbers above include ~30 us of host / autograd time per call)
+from torch.profiler import ProfilerActivity, profile
+
+for fem, shape in ((DiffNet2DFEM(None, domain_size=256), (64, 1, 256, 256)), (DiffNet3DFEM(None, domain_size=64), (16, 1, 64, 64, 64))):
+    u = torch.randn(shape, device=dev, requires_grad=True)
+    out = ops.gp_eval(fem.geometry, u, "N")
+    cot = torch.randn_like(out)
+    torch.autograd.grad(out, u, cot, retain_graph=True)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(10):
+            ops._gp_raw(fem.geometry, u.detach(), 0)
+            torch.autograd.grad(out, u, cot, retain_graph=True)
+        torch.cuda.synchronize()
+    nel = 1
+    for s_ in fem.geometry.elems:
+        nel *= s_
+    nbytes = 4 * u.numel() + 4 * shape[0] * fem.ngp_total * nel
+    for ev in prof.key_averages():
+        if "k_gp_eval" in ev.key:
+            t = ev.device_time_total / ev.count
+            print(f"{fem.nsd}-D kernel {ev.key[:40]:40s} {t:7.1f} us  {nbytes / t / 1e3:6.0f} GB/s  {nbytes / t / 1e3 / peak:.3f} of peak", flush=True)
