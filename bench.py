@@ -350,8 +350,12 @@ def point_of(name, res, peak, clock_mhz=None):
     val = dof / (ms * 1e-3) / 1e9
     ach = val * bpd
     fp32_peak = 148 * 128 * 2 * (clock_mhz or 1965.0) * 1e6 / 1e12      # TFLOP/s, FMA = 2
+    tr = measured_traffic(name) or {}
     return {"value": val, "unit": "GDOF/s", "ms_per_step": ms, "bytes_per_dof": bpd,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_launch": dof * bpd, "traffic": tr.get("bytes"),
+                         "traffic_read": tr.get("dram_read"), "traffic_write": tr.get("dram_write"),
+                         "traffic_source": tr.get("source")},
             "secondary": {"bound": "fp32_pipe", "achieved": val * FLOPS_PER_DOF[nsd] / 1e3, "unit": "TFLOP/s",
                           "peak": fp32_peak, "frac": val * FLOPS_PER_DOF[nsd] / 1e3 / fp32_peak,
                           "algorithmic_flops_per_dof": FLOPS_PER_DOF[nsd]},
