@@ -353,6 +353,8 @@ using namespace dn;
 
 extern "C" {
 
+static int gp_common(const dn_geom* g, int which, int nsd, GpTables* tb);
+
 int dn_abi_version(void) { return DN_ABI_VERSION; }
 const char* dn_last_error(void) { return g_err; }
 int dn_device_check(void) { return device_ok(nullptr); }
@@ -445,7 +447,6 @@ int dn_fem_energy_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* 
   if (int rc = device_ok(&sms)) return rc;
   if (!c) return fail(DN_EINVAL, "consts is NULL");
   if (!g) return fail(DN_EINVAL, "geom is NULL");
-  if (grad_nu) return fail(DN_EINVAL, "grad_nu is not implemented for 3-D");
   double count = 1.0;
   if (c->reduction == 0) {
     long long nelz = g->nz - 1;
@@ -459,8 +460,27 @@ int dn_fem_energy_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* 
   Common cm;
   if (int rc = prepare(u, nu, f, fgp, masks, nmasks, nu_zero_mask, g, c->c_k, c->c_f,
                        c->scale / count, 3, &cm)) return rc;
-  return run3d(cm.u, cm.nu, cm.f, cm.fgp, cm.numask, cm.mk, cm.MK, cm.k, cm.rule, cm.vec4, g,
-               grad_u, 0, 1, workspace, workspace_bytes, loss_out, loss_out_f32, stream, sms);
+  if (grad_nu && !cm.nu.p) return fail(DN_EINVAL, "grad_nu requested without nu");
+  if (int rc = run3d(cm.u, cm.nu, cm.f, cm.fgp, cm.numask, cm.mk, cm.MK, cm.k, cm.rule, cm.vec4, g,
+                     grad_u, 0, 1, workspace, workspace_bytes, loss_out, loss_out_f32, stream, sms)) return rc;
+  if (grad_nu) {        // dL/dnu: a separate gather launch (gp_eval.cu: k_grad_nu_3d)
+    GradNu3 q;
+    memset(&q, 0, sizeof(q));
+    q.u = cm.u; q.numask = cm.numask;
+    for (int i = 0; i < DN_MAX_MASKS; ++i) q.mk[i] = cm.mk[i];
+    q.nmasks = cm.nmasks; q.has_vf = (cm.MK == 4) ? 1 : 0;
+    q.B = g->batch; q.nx = g->nx; q.ny = g->ny; q.nz = g->nz; q.ng = g->ngp_1d;
+    q.zlo = 0; q.zhi = g->nz - 1;
+    if (g->z_own_hi > g->z_own_lo) { q.zlo = g->z_own_lo; q.zhi = g->z_own_hi < g->nz - 1 ? g->z_own_hi : g->nz - 1; }
+    q.coef = (float)(c->scale / count * c->c_k);
+    double gx[4], gw[4];
+    gauss_rule(g->ngp_1d, gx, gw);
+    for (int i = 0; i < 4; ++i) q.w[i] = i < g->ngp_1d ? (float)gw[i] : 0.f;
+    for (int w = 0; w < 4; ++w)
+      if (int rc = gp_common(g, w, 3, &q.tb[w])) return rc;
+    return check_cuda(launch_grad_nu_3d(q, grad_nu, (cudaStream_t)stream), "grad_nu launch");
+  }
+  return DN_OK;
 }
 
 int dn_fem_energy_3d_linked_f32(const dn_field* u, const dn_field* nu, const dn_field* f,

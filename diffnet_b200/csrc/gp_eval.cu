@@ -438,3 +438,94 @@ cudaError_t launch_gp_eval_general_adj(const float* gout, int B, int nsd, int nx
 }
 
 }  // namespace dn
+
+// ---- dL/dnu on 3-D meshes -----------------------------------------------------------------------------------------
+// dL/dnu[n] = S c_k sum over the elements e around node n and their Gauss points g of  w_g N_n(g) |grad u'|^2_g,
+// u' = u with the Dirichlet conditions applied, zero where the nu mask fired (16_topopt.py:124,153 differentiates a
+// 2-D loss w.r.t. nu; the 2-D kernels emit it in the fused launch, this is the 3-D counterpart as a separate gather
+// launch: one thread per node, each adjacent element re-evaluated -- no scratch tensor, no atomics, deterministic;
+// a side path, not tuned).
+namespace dn {
+
+__device__ __forceinline__ float masked_u(const GradNu3& q, int b, int z, int y, int x) {
+  const long long off = (long long)z * q.u.sz + (long long)y * q.u.sy + x;
+  float v = __ldg(q.u.p + (long long)b * q.u.sb + off);
+  for (int m = 0; m < q.nmasks; ++m) {
+    const Field& f = q.mk[m].m;
+    const float mv = __ldg(f.p + (long long)b * f.sb + (long long)z * f.sz + (long long)y * f.sy + x);
+    if (mv > 0.5f) {
+      const Field& vf = q.mk[m].vf;
+      v = (q.has_vf && vf.p) ? __ldg(vf.p + (long long)b * vf.sb + (long long)z * vf.sz + (long long)y * vf.sy + x) : q.mk[m].v;
+    }
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(128) k_grad_nu_3d(GradNu3 q, float* __restrict__ out) {
+  const long long total = (long long)q.B * q.nz * q.ny * q.nx;
+  const int ng = q.ng;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % q.nx);
+    long long r = idx / q.nx;
+    const int y = (int)(r % q.ny);
+    r /= q.ny;
+    const int z = (int)(r % q.nz);
+    const int b = (int)(r / q.nz);
+    float acc = 0.f;
+    bool dead = false;
+    if (q.numask.p)
+      dead = __ldg(q.numask.p + (long long)b * q.numask.sb + (long long)z * q.numask.sz + (long long)y * q.numask.sy + x) > 0.5f;
+    if (!dead) {
+      for (int kb = 0; kb < 2; ++kb) {
+        const int ek = z - kb;
+        if (ek < 0 || ek >= q.nz - 1 || ek < q.zlo || ek >= q.zhi) continue;
+        for (int jb = 0; jb < 2; ++jb) {
+          const int ej = y - jb;
+          if (ej < 0 || ej >= q.ny - 1) continue;
+          for (int ib = 0; ib < 2; ++ib) {
+            const int ei = x - ib;
+            if (ei < 0 || ei >= q.nx - 1) continue;
+            float v[2][2][2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int bq = 0; bq < 2; ++bq)
+#pragma unroll
+                for (int a = 0; a < 2; ++a) v[c][bq][a] = masked_u(q, b, ek + c, ej + bq, ei + a);
+            for (int kg = 0; kg < ng; ++kg)
+              for (int jg = 0; jg < ng; ++jg)
+                for (int ig = 0; ig < ng; ++ig) {
+                  float g3[3];
+#pragma unroll
+                  for (int d = 0; d < 3; ++d) {
+                    const GpTables& t = q.tb[d + 1];
+                    float s = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                      for (int bq = 0; bq < 2; ++bq)
+#pragma unroll
+                        for (int a = 0; a < 2; ++a) s += t.c[2][kg][c] * t.c[1][jg][bq] * t.c[0][ig][a] * v[c][bq][a];
+                    g3[d] = s;
+                  }
+                  const float Nn = q.tb[0].c[2][kg][kb] * q.tb[0].c[1][jg][jb] * q.tb[0].c[0][ig][ib];
+                  acc += q.w[kg] * q.w[jg] * q.w[ig] * Nn * (g3[0] * g3[0] + g3[1] * g3[1] + g3[2] * g3[2]);
+                }
+          }
+        }
+      }
+    }
+    out[idx] = q.coef * acc;
+  }
+}
+
+cudaError_t launch_grad_nu_3d(const GradNu3& q, float* out, cudaStream_t s) {
+  const long long total = (long long)q.B * q.nz * q.ny * q.nx;
+  long long g = (total + 127) / 128;
+  const long long cap = 64LL * sm_count();
+  k_grad_nu_3d<<<(int)(g > cap ? cap : (g < 1 ? 1 : g)), 128, 0, s>>>(q, out);
+  return cudaGetLastError();
+}
+
+}  // namespace dn

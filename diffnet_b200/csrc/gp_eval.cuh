@@ -34,6 +34,18 @@ cudaError_t launch_gp_eval_general(Field in, int B, int nsd, int nx, int ny, int
                                    const float* factors, float* out, cudaStream_t s, int* bad);
 cudaError_t launch_gp_eval_general_adj(const float* gout, int B, int nsd, int nx, int ny, int nz, int nbf_1d,
                                        int ngp_1d, const float* factors, float* gin, cudaStream_t s, int* bad);
+struct GradNu3 {
+  Field u, numask;
+  Mask mk[DN_MAX_MASKS];
+  int nmasks, has_vf;
+  int B, nx, ny, nz, ng;
+  int zlo, zhi;                 // element layers whose energy counts
+  float coef;                   // S * c_k
+  float w[4];                   // 1-D weights
+  GpTables tb[4];               // N, d/dx, d/dy, d/dz factor tables
+};
+
+cudaError_t launch_grad_nu_3d(const GradNu3& q, float* out, cudaStream_t s);
 cudaError_t launch_scale(float* x, size_t n, const float* factor_dev, cudaStream_t s);
 
 }  // namespace dn

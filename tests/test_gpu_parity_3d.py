@@ -387,3 +387,32 @@ def test_linked_slab_launch_loopback_one_gpu(shape):
     assert rel_scalar(ll, lp) < 2e-6
     o = slice(1, nl - 1)
     assert torch.equal(gl.reshape(nl, ny, nx)[o], gp.reshape(nl, ny, nx)[o])
+
+
+@pytest.mark.parametrize("ngp,numask", [(2, False), (3, False), (2, True)])
+def test_grad_nu_3d(ngp, numask):
+    """d loss / d nu in 3-D (the fused launch for loss + dL/du, the gather launch k_grad_nu_3d for dL/dnu):
+    Dirichlet masks applied to u, optional nu mask, grad_output scaling -- against oracle autograd in fp64."""
+    from helpers import oracle_for, to64
+    from oracle import losses as OL
+    B, D, H, W = 2, 7, 9, 12
+    fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_lengths=(1.0, 0.8, 0.5), domain_size=W, ngp_1d=ngp)
+    u, nu, f, src, sink = make_inputs(B, D, H, W, seed=41)
+    d = [(sink, 0.0), (src, 1.0)]
+    kw = dict(nu_zero_mask=src) if numask else {}
+    ud = u.to(DEV).requires_grad_(True)
+    nud = nu.to(DEV).clone().requires_grad_(True)
+    loss = 2.5 * fem.energy_loss(ud, nu=nud, f=f.to(DEV), dirichlet=dev(d), c_k=0.5,
+                                 **{k: v.to(DEV) for k, v in kw.items()})
+    loss.backward()
+    o = oracle_for(fem)
+    u64, nu64 = to64(u).requires_grad_(True), to64(nu).requires_grad_(True)
+    lref = 2.5 * OL.energy_loss(o, u64, nu=nu64, f=to64(f), dirichlet=to64(d), c_k=0.5,
+                                **{k: to64(v) for k, v in kw.items()})
+    gu, gn = torch.autograd.grad(lref, (u64, nu64))
+    assert rel_scalar(loss.cpu(), lref) <= LOSS_RTOL
+    assert rel_l2(ud.grad.cpu(), gu) <= GRAD_RTOL
+    assert rel_l2(nud.grad.cpu(), gn) <= GRAD_RTOL
+    assert float((nud.grad.cpu().double() - gn).abs().max() / gn.abs().max()) <= GRAD_RTOL
+    if numask:
+        assert float(nud.grad.cpu()[src > 0.5].abs().max()) == 0.0

@@ -1,2 +1,2 @@
-DN_DEBUG_PLAN=0 python tools/sweep.py --graph --n 40 poisson3d_128_b1 --cfg "DN_T3_TY=6" --cfg "DN_T3_TY=5" --cfg "DN_T3_TY=4" --cfg "DN_T3_TY=3" --cfg "DN_T3_TY=3 DN_T3_ZC=19" --cfg "DN_T3_TY=3 DN_T3_ZC=26" --cfg "DN_T3_STAGES=3" --cfg "DN_T3_STAGES=6" --cfg "DN_T3_TY=7 DN_T3_ZC=22" --cfg "DN_T3_TY=6 DN_T3_ZC=19" --cfg "DN_T3_LX=32" --cfg "DN_T3_LX=16" 2>&1 | grep -v Warning
-DN_DEBUG_PLAN=0 python tools/sweep.py --graph --n 40 poisson3d_param_64_b16 --cfg "DN_T3_TY=8" --cfg "DN_T3_TY=11" --cfg "DN_T3_TY=13" --cfg "DN_T3_ZC=22" --cfg "DN_T3_ZC=16" --cfg "DN_T3_STAGES=3" --cfg "DN_T3_STAGES=6" 2>&1 | grep -v Warning
+python -m pytest tests/test_gpu_parity_3d.py -m gpu -x -q -k "grad_nu" 2>&1 | tail -8
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
