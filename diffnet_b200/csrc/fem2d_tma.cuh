@@ -352,6 +352,12 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
     else { n = p.bal_q; const int c2 = c - hi; b = c2 / n; ch = c2 - b * n; b += p.bal_rem; }
     r_begin = (int)((long long)ch * p.ny / n);
     r_end = (int)((long long)(ch + 1) * p.ny / n);
+    // every chunk then streams an EVEN number of node rows (its own + the halo rows): whole two-row stages, no
+    // half-empty last stage on the CTA's serial chain.  Interior cuts at odd rows do that when ny is even.
+    if (!(p.ny & 1)) {
+      if (ch > 0) r_begin |= 1;
+      if (ch + 1 < n) r_end |= 1;
+    }
   } else {
     b = blockIdx.x / p.nchunks;
     const int ch = blockIdx.x - b * p.nchunks;
