@@ -22,6 +22,7 @@
 #pragma once
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "dn_common.cuh"
 
@@ -87,6 +88,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+
+// predicated shared-memory store: no divergent branch around a one-lane store
+__device__ __forceinline__ void sts_if(bool pred, float* p, float v) {
+  asm volatile("{\n.reg .pred P;\nsetp.ne.u32 P, %0, 0;\n@P st.shared.f32 [%1], %2;\n}" ::"r"((unsigned)pred), "r"(smem_u32(p)), "f"(v)
+               : "memory");
 }
 
 // ---- float2 helpers (FADD2 / FMUL2 / FFMA2) --------------------------------------------------
@@ -424,12 +431,16 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
     const float2 g23 = mul2(A.a23, row.keep23);
     G = make_float4(g01.x, g01.y, g23.x, g23.y);
   };
-  auto store_row = [&](float4 G, float keep0, float seam_v, int jr) {
-    if (seam_in) G.x += seam_v * keep0;
-    if (jr >= r_begin && act) {
-      if (gout) *reinterpret_cast<float4*>(gout + (long long)(jr - j_first) * nx) = G;
-      if (p.mode != 0) acc += (double)(G.x * G.x + G.y * G.y + G.z * G.z + G.w * G.w);
-    }
+  // branch-free: a predicated 16-byte store, the residual-form square sum selected into `pend` (added to the
+  // fp64 accumulator together with the next stage's energy).  `inr`: the row is owned by this chunk -- a
+  // compile-time true everywhere but in the first stage.
+  const bool wr = act && (gout != nullptr), rs = act && (p.mode != 0);
+  float pend = 0.f;
+  auto store_row = [&](float4 G, float keep0, float seam_v, const int jr, const bool inr) {
+    G.x += seam_in ? seam_v * keep0 : 0.f;
+    if (inr && wr) *reinterpret_cast<float4*>(gout + (long long)(jr - j_first) * nx) = G;
+    const float sq = G.x * G.x + G.y * G.y + G.z * G.z + G.w * G.w;
+    pend += (inr && rs) ? sq : 0.f;
   };
 
   Row2T rowA, rowB;          // even node rows of the chunk live in A, odd ones in B
@@ -437,46 +448,55 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
   accA.a01 = accA.a23 = f2(0.f); accA.a4 = 0.f;
   accB = accA;
 
-  for (int q = 0; q < nst; ++q) {
+  // One stage = two node rows.  The body exists three times: the FIRST stage (no element row above its even
+  // row, the only place a halo row must not be stored), the steady loop (every check of the general body is a
+  // compile-time constant there: one straight-line block per stage between the data wait and the CTA barrier,
+  // so the two rows' shared loads, masks and element pairs can be scheduled across each other), and the trailing
+  // half stage of a chunk that streams an odd number of rows.
+  auto stage = [&](auto first_c, auto odd_c, const int q) {
+    constexpr bool FIRST = decltype(first_c)::value, HAS_ODD = decltype(odd_c)::value;
     mbar_wait(full + st, phase);
     const float* sp = sbase + st * stage_floats;
     const int r0 = 2 * q;                              // even row of this stage (chunk-relative)
-    const bool has_odd = (r0 + 1) < nrows;
     const int par = q & 1;
     float4 G0 = make_float4(0.f, 0.f, 0.f, 0.f), G1 = G0;
     float kp0 = 0.f, kp1 = 0.f, e = 0.f;
 
     // ---- even row -> A; element row (B above, A below); node row r0-1 (B) closes
     F::load_row(p, sp, 2 * nx, has_right, rowA);
-    if (q > 0) {
+    if constexpr (!FIRST) {
       const float e0 = F::elem_row(k, rowB, rowA, vw01, vw23, accB, accA);
-      if (j_first + r0 - 1 >= r_begin) e += e0;
-      if (lane == 31) seam[(par * 2 + 0) * nw + warp] = accB.a4;
+      e += (j_first + r0 - 1 >= r_begin) ? e0 : 0.f;
+      sts_if(lane == 31, seam + (par * 2 + 0) * nw + warp, accB.a4);
       close_row(accB, rowB, G0);
       kp0 = rowB.keep01.x;
     }
     // ---- odd row -> B; element row (A above, B below); node row r0 (A) closes
-    if (has_odd) {
+    if constexpr (HAS_ODD) {
       F::load_row(p, sp + nx, 2 * nx, has_right, rowB);
       const float e1 = F::elem_row(k, rowA, rowB, vw01, vw23, accA, accB);
-      if (j_first + r0 >= r_begin) e += e1;
-      if (lane == 31) seam[(par * 2 + 1) * nw + warp] = accA.a4;
+      e += (j_first + r0 >= r_begin) ? e1 : 0.f;
+      sts_if(lane == 31, seam + (par * 2 + 1) * nw + warp, accA.a4);
       close_row(accA, rowA, G1);
       kp1 = rowA.keep01.x;
     }
-    if (p.mode == 0 && act) acc += (double)e;
+    acc += (double)(((p.mode == 0 && act) ? e : 0.f) + pend);
+    pend = 0.f;
     __syncthreads();      // stage consumed by every thread; seam words of both rows visible
     if (issued < nst) issue_stage();
     ++st;
     if (st == S) { st = 0; phase ^= 1u; }
-    float s0 = 0.f, s1 = 0.f;
-    if (seam_in) {
-      s0 = seam[(par * 2 + 0) * nw + warp - 1];
-      s1 = seam[(par * 2 + 1) * nw + warp - 1];
-    }
-    if (q > 0) store_row(G0, kp0, s0, j_first + r0 - 1);
-    if (has_odd) store_row(G1, kp1, s1, j_first + r0);
-  }
+    // unconditional loads from a valid slot (warp 0 reads its own), selected away where there is no seam
+    const int wl = warp > 0 ? warp - 1 : 0;
+    const float s0 = seam[(par * 2 + 0) * nw + wl];
+    const float s1 = seam[(par * 2 + 1) * nw + wl];
+    if constexpr (!FIRST) store_row(G0, kp0, s0, j_first + r0 - 1, true);
+    if constexpr (HAS_ODD) store_row(G1, kp1, s1, j_first + r0, FIRST ? (j_first >= r_begin) : true);
+  };
+  const int nfull = nrows >> 1;                        // >= 1: a chunk streams at least two rows
+  stage(std::true_type{}, std::true_type{}, 0);
+  for (int q = 1; q < nfull; ++q) stage(std::false_type{}, std::true_type{}, q);
+  if (nrows & 1) stage(std::false_type{}, std::false_type{}, nfull);
 
   // ---- last node row of the image: no element row below it; its sum is already complete
   if (r_end == p.ny) {
@@ -489,8 +509,9 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
     close_row(A, row, G);
     __syncthreads();
     const float sv = seam_in ? seam[(par * 2) * nw + warp - 1] : 0.f;
-    store_row(G, row.keep01.x, sv, p.ny - 1);
+    store_row(G, row.keep01.x, sv, p.ny - 1, true);
   }
+  acc += (double)pend;
 
   // all streaming done: the next grid in the stream may start launching behind our epilogue
   // (its own pdl_wait() still holds it until this grid has completed and flushed)
