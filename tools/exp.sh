@@ -1,5 +1,3 @@
-for lib in variants/lib_seam.so diffnet_b200/lib/libdiffnet_fem.so variants/lib_seam.so diffnet_b200/lib/libdiffnet_fem.so; do
-  echo "=== lib $lib"
-  DIFFNET_FEM_LIB=$PWD/$lib python tools/sweep.py --graph --n 80 poisson2d_param_256_b64 poisson2d_512_b16 ibn2d_512_b16 poisson2d_64_b1 2>&1 | grep -v Warning
-done
-python -m pytest tests/test_gpu_parity_2d.py -m gpu -x -q 2>&1 | tail -1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -1
+python tools/fuzz_parity.py 90 23 2>&1 | tail -1
+python bench.py --no-cpu --train-steps 0 > gpurun_out/r2h_bench.json 2>/dev/null; python tools/show_bench.py gpurun_out/r2h_bench.json | head -13
