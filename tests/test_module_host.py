@@ -41,8 +41,12 @@ def test_reference_kwargs_and_state_dict_keys():
     assert not any(p.requires_grad for p in m.parameters())
     # ngp_1d below 2 is lifted to 2 for Q1 (DiffNetFEM.py:29-38)
     assert DiffNet2DFEM(None, ngp_1d=1).ngp_1d == 2
+    # degree 2 / 3 are built (general-basis ops); like the reference they need (domain_size - 1) % degree == 0
+    with pytest.raises(AssertionError):
+        DiffNet2DFEM(None, fem_basis_deg=2)                 # default domain_size 64: 63 % 2 != 0
+    assert DiffNet2DFEM(None, fem_basis_deg=2, domain_size=65).nbf_1d == 3
     with pytest.raises(NotImplementedError):
-        DiffNet2DFEM(None, fem_basis_deg=2)
+        DiffNet2DFEM(None, fem_basis_deg=4)
 
 
 def test_user_subclass_contract():

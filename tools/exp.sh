@@ -1,1 +1,1 @@
-python tools/sweep.py --graph --n 80 poisson2d_param_256_b64 poisson2d_512_b16 --cfg "DN_T2_STAGES=3" --cfg "DN_T2_STAGES=4" --cfg "DN_T2_FILL_PCT=60" --cfg "DN_T2_FILL_PCT=65" --cfg "DN_T2_FILL_PCT=75" --cfg "DN_T2_FILL_PCT=80" --cfg "DN_T2_FILL_PCT=100" --cfg "DN_T2_STAGES=3 DN_T2_FILL_PCT=60" --cfg "DN_PDL=0" 2>&1 | grep -v Warning
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
