@@ -511,3 +511,27 @@ def test_gp_eval_marching_kernels_against_oracle(B, H, W, ngp):
     sum((fn(u2) * c.to(DEV)).sum() for fn, c in zip((fem.gauss_pt_evaluation, fem.gauss_pt_evaluation_der_x,
                                                      fem.gauss_pt_evaluation_der_y), cot)).backward()
     assert rel_l2(u2.grad, ud.grad) <= 1e-6
+
+
+@pytest.mark.parametrize("B,H,W", [(40, 128, 64), (64, 256, 64), (100, 300, 32), (23, 510, 128), (16, 512, 256)])
+def test_balanced_one_wave_split_against_the_general_kernel(B, H, W):
+    """Launch shapes the one-wave planner cuts into equal parts per image (a subset of the slots, interior cuts
+    at odd rows, images with q and q + 1 chunks): every row must be owned by exactly one chunk.  Cross-checked
+    against the general kernel (a different decomposition) and against the forced uniform split."""
+    fem = DiffNet2DFEM(None, domain_sizes=(W, H, 1), domain_size=W)
+    g = torch.Generator().manual_seed(B * 7 + H)
+    u = torch.randn(B, 1, H, W, generator=g).to(DEV)
+    nu = torch.exp(0.3 * torch.randn(B, 1, H, W, generator=g)).to(DEV)
+    f = torch.randn(B, 1, H, W, generator=g).to(DEV)
+    bc = (torch.rand(B, 1, H, W, generator=g) > 0.9).float().to(DEV)
+    kw = dict(nu=nu, f=f, dirichlet=[(bc, 0.5)])
+    ls, gs = fem.energy_loss_and_grad(u, **kw)
+    for knobs in ({"DN_2D_PATH": "warp"}, {"DN_T2_BALANCE": "0"}, {"DN_T2_FILL_PCT": "100"}, {"DN_T2_FILL_PCT": "45"}):
+        os.environ.update(knobs)
+        try:
+            lo, go = fem.energy_loss_and_grad(u, **kw)
+        finally:
+            for k in knobs:
+                os.environ.pop(k)
+        assert rel_scalar(ls, lo) < 2e-6, knobs
+        assert rel_l2(gs, go) < 2e-6 and float((gs - go).abs().max() / go.abs().max()) < 1e-5, knobs
