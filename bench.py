@@ -41,6 +41,9 @@ WORKLOADS = {
     "poisson3d_param_64_b16": (3, 64, 16, 20, "Poisson 3D parametric 64^3 Q1 hex, batch 16/GPU (u, source, sink, f)"),
     "poisson3d_128_b1": (3, 128, 1, 24, "Poisson 3D 128^3, variable nu, f, two masks (roofline point)"),
     "poisson3d_256_b1": (3, 256, 1, 20, "Poisson 3D non-parametric 256^3 (u, nu, bc1, f)"),
+    # forcing given AT the Gauss points (e8_2d_poisson_mms.py:154-175): streamed as an assembled load vector (4 B/node)
+    "mms2d_fgp_256_b64": (2, 256, 64, 24, "Poisson 2D 256x256, batch 64/GPU, forcing at the Gauss points (u, nu, b(f_gp), bc1, bc2)"),
+    "mms3d_fgp_64_b16": (3, 64, 16, 20, "Poisson 3D 64^3, batch 16/GPU, nu == 1, forcing at the Gauss points (u, b(f_gp), source, sink)"),
     # one 256^3 field split into z-slabs over the ranks (strong scaling; halo exchange + loss all-reduce)
     "poisson3d_256_slab": (3, 256, 1, 20, "Poisson 3D non-parametric 256^3, z-slabs over all ranks, 1-plane halo exchange"),
 }
@@ -123,9 +126,18 @@ def make_inputs(name, device, seed):
     if nsd == 2:
         gen = ibn2d_batch if name.startswith("ibn2d") else poisson2d_parametric_batch
         u, inputs, f = gen(B, size, device, seed)
+        if name.startswith("mms"):
+            g = torch.Generator(device="cpu").manual_seed(seed + 11)
+            f_gp = torch.randn(B, 4, size - 1, size - 1, generator=g).to(device)
+            return dict(u=u, nu=inputs[:, 0:1], f_gp=f_gp, dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)],
+                        c_k=0.5, _fields=[u, inputs, f_gp])
         return dict(u=u, nu=inputs[:, 0:1], f=f, dirichlet=[(inputs[:, 1:2], 1.0), (inputs[:, 2:3], 0.0)],
                     _fields=[u, inputs, f])
     u, src, sink, f = poisson3d_parametric_batch(B, size, device, seed)
+    if name.startswith("mms"):
+        g = torch.Generator(device="cpu").manual_seed(seed + 11)
+        f_gp = torch.randn(B, 8, size - 1, size - 1, size - 1, generator=g).to(device)
+        return dict(u=u, f_gp=f_gp, dirichlet=[(sink, 0.0), (src, 1.0)], c_k=0.5, _fields=[u, src, sink, f_gp])
     if name == "poisson3d_param_64_b16":       # IBN_3D.py:114-136: nu == 1
         return dict(u=u, f=f, dirichlet=[(sink, 0.0), (src, 1.0)], _fields=[u, src, sink, f])
     g = torch.Generator(device="cpu").manual_seed(seed + 7)
@@ -363,7 +375,7 @@ def point_of(name, res, peak, clock_mhz=None):
 
 
 POINTS = ["poisson2d_512_b16", "ibn2d_512_b16", "poisson3d_param_64_b16", "poisson3d_128_b1", "poisson3d_256_b1",
-          "poisson2d_64_b1"]
+          "poisson2d_64_b1", "mms2d_fgp_256_b64", "mms3d_fgp_64_b16"]
 
 
 # ------------------------------------------------------------------------------------ oracle legs
@@ -494,6 +506,46 @@ def run_reference(args):
     }))
 
 
+def numa_local(dev_index):
+    """Before the pinned host buffers of the e2e leg are allocated: run this rank on the cores of the NUMA node its
+    GPU hangs off and prefer that node's memory, so that eight ranks do not all stream their inputs out of one
+    socket's DRAM.  Best effort (sysfs may not expose the topology in a VM, set_mempolicy may be filtered): what was
+    done is returned for the JSON line, failures leave the process as it was."""
+    info = {"node": None, "cpus": None, "mempolicy": None}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+        info["cpus"] = len(use) if use else 0
+        try:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238          # x86-64
+            rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+            info["mempolicy"] = "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
+        except Exception as e:   # noqa: BLE001
+            info["mempolicy"] = f"{type(e).__name__}"
+    except Exception as e:   # noqa: BLE001
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
+
+
 # ------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -535,6 +587,7 @@ def run_ours(args):
     value = dof_step * world / (ms_step * 1e-3) / 1e9
 
     # ---- e2e: public API, pinned host inputs, H2D + launch + D2H(loss) every step
+    numa = numa_local(local)
     hs = sets[0]
     host = [f.detach().cpu().pin_memory() for f in hs["_fields"]]
     devbuf = [torch.empty_like(f) for f in hs["_fields"]]
@@ -694,6 +747,18 @@ def run_ours(args):
                 cr = copy_reference(dev, pB * psize ** pnsd * pbpd)
                 points[pn]["roofline"]["same_bytes_copy"] = cr
                 points[pn]["roofline"]["frac_of_same_bytes_copy"] = points[pn]["roofline"]["achieved"] / cr["achieved"]
+                if pn.startswith("mms"):       # the same call with f_gp read by the general kernels every step
+                    from diffnet_b200 import ops as _ops
+                    _ops.USE_LOAD_VECTOR = False
+                    try:
+                        r = time_workload(pn, dev, 4321, 20, 5, 3)
+                        points[pn]["f_gp_in_general_kernel_ms"] = r["ms_step"]
+                        points[pn]["note"] = ("f_gp is assembled ONCE into a load vector b (dn_fem_load_vector_f32, cached "
+                                              "per tensor version); the timed step streams b.  f_gp_in_general_kernel_ms: the "
+                                              "same call with f_gp read at the Gauss points every step (DN_LOAD_VECTOR=0)")
+                        del r
+                    finally:
+                        _ops.USE_LOAD_VECTOR = True
             except Exception as e:   # noqa: BLE001  (the headline must still be printed)
                 points[pn] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
@@ -770,7 +835,7 @@ def run_ours(args):
                                                "(register-operand dispatch), 2-D by HBM"}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": Ke, "h2d_gbs_per_gpu": h2d * Ke / float(te.item()) / 1e9,
+                    "steps": Ke, "h2d_gbs_per_gpu": h2d * Ke / float(te.item()) / 1e9, "numa": numa,
                     "note": "pinned host -> device copy of all input fields + fused launch + loss.item() every step, double-buffered (the next step's copy overlaps this step's launch and read-back); CUDA events around the steps, max over ranks"},
             "e2e_compact_inputs": e2e_compact,
             "e2e_device_producers": e2e_prod,

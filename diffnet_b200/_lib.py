@@ -13,7 +13,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DIFFNET_FEM_LIB", os.path.join(PKG, "lib", "libdiffnet_fem.so"))
 
 DN_MAX_MASKS = 3
-DN_OK, DN_EINVAL, DN_EARCH, DN_ECUDA, DN_EWORKSPACE = 0, -1, -2, -3, -4
+DN_OK, DN_EINVAL, DN_EARCH, DN_ECUDA, DN_EWORKSPACE, DN_ENOSTREAM = 0, -1, -2, -3, -4, -5
+DN_F_LOAD_VECTOR = 1
 
 
 class dn_field(C.Structure):
@@ -35,7 +36,7 @@ class dn_geom(C.Structure):
 
 class dn_consts(C.Structure):
     _fields_ = [("c_k", C.c_double), ("c_f", C.c_double), ("scale", C.c_double),
-                ("reduction", C.c_int32), ("_pad", C.c_int32)]
+                ("reduction", C.c_int32), ("flags", C.c_int32)]
 
 
 class dn_slab_link(C.Structure):
@@ -85,6 +86,7 @@ PROTOTYPES = {
                                              _P(C.c_float), C.c_void_p, C.c_void_p]),
     "dn_fem_gp_eval_general_adj_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  _P(C.c_float), C.c_void_p, C.c_void_p]),
+    "dn_fem_load_vector_f32": (C.c_int, [_P(dn_field), _P(dn_geom), C.c_void_p, C.c_void_p]),
     "dn_gen_kl_table_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "dn_gen_kl_inputs_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_double), C.c_double, C.c_int, C.c_int,
                                        C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -110,7 +112,7 @@ _lib = None
 
 
 class DiffNetFEMError(RuntimeError):
-    pass
+    code = None        # the dn_status the library returned, when the error came from a call
 
 
 def lib():
@@ -133,4 +135,6 @@ def lib():
 def check(rc: int, what: str):
     if rc != DN_OK:
         msg = lib().dn_last_error()
-        raise DiffNetFEMError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+        err = DiffNetFEMError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+        err.code = rc
+        raise err

@@ -106,7 +106,7 @@ struct Common {
 
 static int prepare(const dn_field* u, const dn_field* nu, const dn_field* f, const dn_field* fgp,
                    const dn_mask* masks, int nmasks, const dn_field* nu_zero_mask,
-                   const dn_geom* g, double c_k, double c_f, double S, int nsd, Common* c) {
+                   const dn_geom* g, double c_k, double c_f, double S, int nsd, Common* c, int flags = 0) {
   if (!g) return fail(DN_EINVAL, "geom is NULL");
   if (g->nsd != nsd) return fail(DN_EINVAL, "geom.nsd=%d but the %d-D entry point was called", g->nsd, nsd);
   if (g->batch < 1 || g->nx < 2 || g->ny < 2 || (nsd == 3 && g->nz < 2))
@@ -116,6 +116,7 @@ static int prepare(const dn_field* u, const dn_field* nu, const dn_field* f, con
     return fail(DN_EINVAL, "element sizes must be positive");
   if (!u || !u->ptr) return fail(DN_EINVAL, "u is NULL");
   if (f && f->ptr && fgp && fgp->ptr) return fail(DN_EINVAL, "give f or fgp, not both");
+  if ((flags & DN_F_LOAD_VECTOR) && !(f && f->ptr)) return fail(DN_EINVAL, "DN_F_LOAD_VECTOR needs the load vector in f");
   if (nmasks < 0 || nmasks > DN_MAX_MASKS)
     return fail(DN_EINVAL, "nmasks=%d (max %d)", nmasks, DN_MAX_MASKS);
   if (nmasks > 0 && !masks) return fail(DN_EINVAL, "masks is NULL");
@@ -150,6 +151,8 @@ static int prepare(const dn_field* u, const dn_field* nu, const dn_field* f, con
   c->k.kz = (nsd == 3) ? (float)(S * c_k * Wn * (2.0 / g->hz) * (2.0 / g->hz) / nrm) : 0.f;
   c->k.kf = (float)(S * c_f * Wn / ((nsd == 2) ? 16.0 : 64.0));
   c->k.t = (float)t;
+  c->k.kb = (float)(S * c_f);
+  c->k.lv = (flags & DN_F_LOAD_VECTOR) ? 1 : 0;
   c->rule.n = g->ngp_1d;
   for (int i = 0; i < 4; ++i) {
     c->rule.x[i] = i < g->ngp_1d ? (float)gx[i] : 0.f;
@@ -276,7 +279,7 @@ static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, int m
   const char* path = getenv("DN_2D_PATH");
   if (path && !strcmp(path, "warp")) return DN_OK;
   if (!c.vec4 || c.fgp.p || ((uintptr_t)grad % 16 != 0)) return DN_OK;
-  const int NU = c.nu.p ? 1 : 0, F = c.f.p ? 1 : 0, NMK = c.numask.p ? 1 : 0;
+  const int NU = c.nu.p ? 1 : 0, F = c.f.p ? (c.k.lv ? 2 : 1) : 0, NMK = c.numask.p ? 1 : 0;
   if (g->nx % 4 != 0 || g->nx / 4 > DN_T2_MAXT) return DN_OK;
   int MKx = c.MK;
   if (!mask_input) {                     // operator apply: only the plain-mask, no-source variants exist
@@ -314,6 +317,7 @@ static int run2t(const Common& c, const dn_geom* g, float* grad, int mode, int m
   p.k2.nkf = make_float2(-kf, -kf); p.k2.nkft = make_float2(-kf * t, -kf * t);
   p.k2.nkftt = make_float2(-kf * t * t, -kf * t * t);
   p.k2.c0x_const = make_float2(4.f * kx, 4.f * kx); p.k2.c0y_const = make_float2(4.f * ky, 4.f * ky);
+  p.k2.nkb = make_float2(-c.k.kb, -c.k.kb);
   p.grad = grad;
   p.red.counter = (unsigned int*)workspace;
   p.red.partials = (double*)((char*)workspace + 64);
@@ -332,6 +336,9 @@ static int run2d(const Common& c, const dn_geom* g, float* grad, float* grad_nu,
     int rc = run2t(c, g, grad, mode, mask_input, workspace, wsb, loss_out, loss_f32, stream, sms, &handled);
     if (rc != DN_OK || handled) return rc;
   }
+  if (c.k.lv)
+    return fail(DN_ENOSTREAM, "DN_F_LOAD_VECTOR: the streaming 2-D kernel cannot take this launch (nx %% 4, nx <= %d, "
+                "16-byte aligned dense rows, no grad_nu); pass f_gp instead", 4 * DN_T2_MAXT);
   bool vec4 = c.vec4 && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)grad_nu % 16 == 0);
   Plan2D pl = plan2d(g, vec4, sms);
   if (!workspace || wsb < ws_bytes_for_grid(pl.grid))
@@ -426,7 +433,7 @@ int dn_fem_energy_2d_f32(const dn_field* u, const dn_field* nu, const dn_field* 
       : 1.0;
   Common cm;
   if (int rc = prepare(u, nu, f, fgp, masks, nmasks, nu_zero_mask, g, c->c_k, c->c_f,
-                       c->scale / count, 2, &cm)) return rc;
+                       c->scale / count, 2, &cm, c->flags)) return rc;
   if (grad_nu && !cm.nu.p) return fail(DN_EINVAL, "grad_nu requested without nu");
   return run2d(cm, g, grad_u, grad_nu, 0, 1, workspace, workspace_bytes, loss_out, loss_out_f32,
                stream, sms);
@@ -469,7 +476,7 @@ int dn_fem_energy_3d_f32(const dn_field* u, const dn_field* nu, const dn_field* 
   }
   Common cm;
   if (int rc = prepare(u, nu, f, fgp, masks, nmasks, nu_zero_mask, g, c->c_k, c->c_f,
-                       c->scale / count, 3, &cm)) return rc;
+                       c->scale / count, 3, &cm, c->flags)) return rc;
   if (grad_nu && !cm.nu.p) return fail(DN_EINVAL, "grad_nu requested without nu");
   if (int rc = run3d(cm.u, cm.nu, cm.f, cm.fgp, cm.numask, cm.mk, cm.MK, cm.k, cm.rule, cm.vec4, g,
                      grad_u, 0, 1, workspace, workspace_bytes, loss_out, loss_out_f32, stream, sms)) return rc;
@@ -648,6 +655,27 @@ int dn_fem_gp_eval_general_adj_f32(const float* grad_out, int nsd, int batch, in
                                              (cudaStream_t)stream, &bad);
   if (bad) return fail(DN_EINVAL, "gp_eval_general_adj: nsd 1..3, nbf_1d 2..4, ngp_1d 1..4, (nodes - 1) %% (nbf_1d - 1) == 0");
   return check_cuda(e, "gp_eval_general_adj launch");
+}
+
+int dn_fem_load_vector_f32(const dn_field* fgp, const dn_geom* g, float* out, void* stream) {
+  if (int rc = device_ok(nullptr)) return rc;
+  if (!g) return fail(DN_EINVAL, "geom is NULL");
+  if (!fgp || !fgp->ptr || !out) return fail(DN_EINVAL, "load_vector: NULL input/output");
+  if ((g->nsd != 2 && g->nsd != 3) || g->batch < 1 || g->nx < 2 || g->ny < 2 || (g->nsd == 3 && g->nz < 2))
+    return fail(DN_EINVAL, "load_vector: nsd 2 or 3, batch >= 1, >= 2 nodes per direction");
+  double gx[4], gw[4];
+  if (gauss_rule(g->ngp_1d, gx, gw)) return fail(DN_EINVAL, "ngp_1d=%d (2..4)", g->ngp_1d);
+  LoadVec q;
+  memset(&q, 0, sizeof(q));
+  q.fgp = (const float*)fgp->ptr;
+  q.sb = fgp->stride_b;
+  q.B = (fgp->stride_b == 0) ? 1 : g->batch;
+  q.nx = g->nx; q.ny = g->ny; q.nz = g->nsd == 3 ? g->nz : 1; q.nsd = g->nsd; q.ng = g->ngp_1d;
+  for (int i = 0; i < g->ngp_1d; ++i) {
+    q.wn[0][i] = (float)(gw[i] * 0.5 * (1.0 - gx[i]));
+    q.wn[1][i] = (float)(gw[i] * 0.5 * (1.0 + gx[i]));
+  }
+  return check_cuda(launch_load_vector(q, out, (cudaStream_t)stream), "load_vector launch");
 }
 
 int dn_peer_alloc(size_t bytes, void** ptr) {

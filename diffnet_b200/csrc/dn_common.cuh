@@ -41,6 +41,8 @@ struct Reduce {
 //   t = second moment of the 1-D Gauss rule (1/3 for the 2-point rule).
 struct Consts {
   float kx, ky, kz, kf, t;
+  float kb;   // S c_f: weight of an assembled load vector
+  int lv;     // `f` is an assembled load vector (dn_consts.flags & DN_F_LOAD_VECTOR): streaming kernels only
 };
 
 // 1-D quadrature tables, only used by the f-at-Gauss-points path.

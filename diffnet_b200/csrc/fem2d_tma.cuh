@@ -34,6 +34,7 @@ namespace dn {
 // Packed constants of one launch (see prepare(): kx, ky carry S c_k W (2/h)^2 / 64, kf = S c_f W / 16)
 struct K2 {
   float2 kx, ky, kxt, kyt, t, nkf, nkft, nkftt, c0x_const, c0y_const;
+  float2 nkb;   // -(S c_f): weight of an assembled load vector (FK == 2)
 };
 
 struct P2T {
@@ -175,6 +176,8 @@ __device__ __forceinline__ float2 elem_pair(const K2& k, float2 st, float2 dt, f
 struct Row2T {
   RowSD u, n, f;
   float2 keep01, keep23;
+  float2 lb01, lb23;   // FK == 2: -(S c_f) b of the 4 own nodes (their gradient share), and
+  float lE;            //          their energy share sum(-(S c_f) b u)
 };
 // Gradient accumulators of one node row: own nodes 0..3 and the right neighbour's node 0.
 struct Acc2T {
@@ -182,10 +185,14 @@ struct Acc2T {
   float a4;
 };
 
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI = true>
+// FK: 0 no source term, 1 nodal source f (interpolated to the Gauss points), 2 `f` is an ASSEMBLED load vector
+// b_a = sum_g w_g |J| N_a(g) f_g (dn_fem_load_vector_f32): the term -c_f sum_a b_a u_a is added per node when its
+// row closes -- what the reference's f-at-Gauss-points form (e8_2d_poisson_mms.py:154-175) costs once b exists.
+template <int NM, bool VF, bool HAS_NU, int FK, bool NUMASK, bool MI = true>
 struct Fem2T {
-  static constexpr int NF = 1 + (HAS_NU ? 1 : 0) + (HAS_F ? 1 : 0) + (NUMASK ? 1 : 0) + NM + (VF ? 1 : 0);
-  static constexpr int F_U = 0, F_NU = 1, F_F = F_NU + (HAS_NU ? 1 : 0), F_NM = F_F + (HAS_F ? 1 : 0),
+  static constexpr bool HAS_F = (FK == 1), LV = (FK == 2);
+  static constexpr int NF = 1 + (HAS_NU ? 1 : 0) + (FK ? 1 : 0) + (NUMASK ? 1 : 0) + NM + (VF ? 1 : 0);
+  static constexpr int F_U = 0, F_NU = 1, F_F = F_NU + (HAS_NU ? 1 : 0), F_NM = F_F + (FK ? 1 : 0),
                        F_M = F_NM + (NUMASK ? 1 : 0), F_VF = F_M + NM;
 
   // Read one node row from its ring stage (own 4 nodes + right neighbour of every field), apply
@@ -218,10 +225,16 @@ struct Fem2T {
         if constexpr (NUMASK) n = (v[F_NM][e] > 0.5f) ? 0.f : n;
         nb[e] = n;
       }
-      if constexpr (HAS_F) fb[e] = v[F_F][e];
+      if constexpr (HAS_F || LV) fb[e] = v[F_F][e];
     }
     o.keep01 = f2(kp[0], kp[1]);
     o.keep23 = f2(kp[2], kp[3]);
+    if constexpr (LV) {
+      o.lb01 = mul2(p.k2.nkb, f2(fb[0], fb[1]));
+      o.lb23 = mul2(p.k2.nkb, f2(fb[2], fb[3]));
+      const float2 le = fma2(o.lb01, f2(ub[0], ub[1]), mul2(o.lb23, f2(ub[2], ub[3])));
+      o.lE = le.x + le.y;
+    }
     o.u = row_sd(ub);
     // the last element of a row does not exist: E and g are linear in (nu, f), so zeroing their
     // x-sums/differences for that element removes it (nu == 1 uses the weight vw instead)
@@ -336,9 +349,9 @@ __device__ __forceinline__ void finish_loss_w0(const Reduce& r, double cta_value
 }
 
 // TB = max threads per CTA, MINB = min resident CTAs per SM the register allocation must allow.
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI, int TB, int MINB>
+template <int NM, bool VF, bool HAS_NU, int FK, bool NUMASK, bool MI, int TB, int MINB>
 __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ P2T p) {
-  using F = Fem2T<NM, VF, HAS_NU, HAS_F, NUMASK, MI>;
+  using F = Fem2T<NM, VF, HAS_NU, FK, NUMASK, MI>;
   constexpr int NF = F::NF;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[TB / 32];
@@ -425,22 +438,24 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
   // left lane now (across a warp seam it arrives through shared memory after the barrier).
   auto close_row = [&](const Acc2T& A, const Row2T& row, float4& G) {
     const float fromL = __shfl_up_sync(0xffffffffu, A.a4, 1);
-    float2 g01 = A.a01;
+    float2 g01 = A.a01, g23 = A.a23;
     if (lane > 0) g01.x += fromL;
+    if constexpr (F::LV) { g01 = add2(g01, row.lb01); g23 = add2(g23, row.lb23); }
     g01 = mul2(g01, row.keep01);
-    const float2 g23 = mul2(A.a23, row.keep23);
+    g23 = mul2(g23, row.keep23);
     G = make_float4(g01.x, g01.y, g23.x, g23.y);
   };
   // branch-free: a predicated 16-byte store, the residual-form square sum selected into `pend` (added to the
   // fp64 accumulator together with the next stage's energy).  `inr`: the row is owned by this chunk -- a
   // compile-time true everywhere but in the first stage.
-  const bool wr = act && (gout != nullptr), rs = act && (p.mode != 0);
+  const bool wr = act && (gout != nullptr), rs = act && (p.mode != 0), en = act && (p.mode == 0);
   float pend = 0.f;
-  auto store_row = [&](float4 G, float keep0, float seam_v, const int jr, const bool inr) {
+  auto store_row = [&](float4 G, float keep0, float seam_v, const int jr, const bool inr, const float le) {
     G.x += seam_in ? seam_v * keep0 : 0.f;
     if (inr && wr) *reinterpret_cast<float4*>(gout + (long long)(jr - j_first) * nx) = G;
     const float sq = G.x * G.x + G.y * G.y + G.z * G.z + G.w * G.w;
     pend += (inr && rs) ? sq : 0.f;
+    if constexpr (F::LV) pend += (inr && en) ? le : 0.f;      // the row's load-vector energy, once, by its owner
   };
 
   Row2T rowA, rowB;          // even node rows of the chunk live in A, odd ones in B
@@ -460,7 +475,7 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
     const int r0 = 2 * q;                              // even row of this stage (chunk-relative)
     const int par = q & 1;
     float4 G0 = make_float4(0.f, 0.f, 0.f, 0.f), G1 = G0;
-    float kp0 = 0.f, kp1 = 0.f, e = 0.f;
+    float kp0 = 0.f, kp1 = 0.f, e = 0.f, le0 = 0.f, le1 = 0.f;
 
     // ---- even row -> A; element row (B above, A below); node row r0-1 (B) closes
     F::load_row(p, sp, 2 * nx, has_right, rowA);
@@ -470,6 +485,7 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
       sts_if(lane == 31, seam + (par * 2 + 0) * nw + warp, accB.a4);
       close_row(accB, rowB, G0);
       kp0 = rowB.keep01.x;
+      if constexpr (F::LV) le0 = rowB.lE;
     }
     // ---- odd row -> B; element row (A above, B below); node row r0 (A) closes
     if constexpr (HAS_ODD) {
@@ -479,6 +495,7 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
       sts_if(lane == 31, seam + (par * 2 + 1) * nw + warp, accA.a4);
       close_row(accA, rowA, G1);
       kp1 = rowA.keep01.x;
+      if constexpr (F::LV) le1 = rowA.lE;
     }
     acc += (double)(((p.mode == 0 && act) ? e : 0.f) + pend);
     pend = 0.f;
@@ -490,8 +507,8 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
     const int wl = warp > 0 ? warp - 1 : 0;
     const float s0 = seam[(par * 2 + 0) * nw + wl];
     const float s1 = seam[(par * 2 + 1) * nw + wl];
-    if constexpr (!FIRST) store_row(G0, kp0, s0, j_first + r0 - 1, true);
-    if constexpr (HAS_ODD) store_row(G1, kp1, s1, j_first + r0, FIRST ? (j_first >= r_begin) : true);
+    if constexpr (!FIRST) store_row(G0, kp0, s0, j_first + r0 - 1, true, le0);
+    if constexpr (HAS_ODD) store_row(G1, kp1, s1, j_first + r0, FIRST ? (j_first >= r_begin) : true, le1);
   };
   const int nfull = nrows >> 1;                        // >= 1: a chunk streams at least two rows
   stage(std::true_type{}, std::true_type{}, 0);
@@ -509,7 +526,9 @@ __global__ void __launch_bounds__(TB, MINB) k_fem2d_tma(const __grid_constant__ 
     close_row(A, row, G);
     __syncthreads();
     const float sv = seam_in ? seam[(par * 2) * nw + warp - 1] : 0.f;
-    store_row(G, row.keep01.x, sv, p.ny - 1, true);
+    float le = 0.f;
+    if constexpr (F::LV) le = row.lE;
+    store_row(G, row.keep01.x, sv, p.ny - 1, true, le);
   }
   acc += (double)pend;
 
@@ -544,15 +563,15 @@ constexpr int kMaxDynSmem = 226 * 1024;   // 227 KB per CTA minus the kernels' s
 // One register budget (<= 128 registers, CTAs of up to 512 threads).  A tighter variant
 // (<= 96 registers, 10 instead of 8 resident 64-thread CTAs per SM) measured 10% SLOWER on
 // 256^2 x 64: more CTAs per wave means shorter row chunks and more seam work (profiles/).
-template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int MK, bool HAS_NU, int FK, bool NUMASK>
 struct Kern2T {
   // MK 0..3: that many scalar-valued masks; 4: one mask with a value field; 5..7: 1..3 masks whose
   // values are NOT substituted into u (mask_input = 0: the operator v -> mask(K v) of the resmin backward)
   static constexpr int NM = (MK == 4) ? 1 : (MK >= 5 ? MK - 4 : MK);
-  static auto get() { return k_fem2d_tma<NM, (MK == 4), HAS_NU, HAS_F, NUMASK, (MK < 5), DN_T2_MAXT, 1>; }
+  static auto get() { return k_fem2d_tma<NM, (MK == 4), HAS_NU, FK, NUMASK, (MK < 5), DN_T2_MAXT, 1>; }
 };
 
-template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int MK, bool HAS_NU, int FK, bool NUMASK>
 cudaError_t prep2t() {
   // opt in to the full dynamic shared memory once per device
   static bool done[64] = {};
@@ -560,15 +579,15 @@ cudaError_t prep2t() {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  e = cudaFuncSetAttribute(Kern2T<MK, HAS_NU, HAS_F, NUMASK>::get(),
+  e = cudaFuncSetAttribute(Kern2T<MK, HAS_NU, FK, NUMASK>::get(),
                            cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
   if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
   return e;
 }
 
-template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int MK, bool HAS_NU, int FK, bool NUMASK>
 cudaError_t launch2t(const P2T& p, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
-  cudaError_t e = prep2t<MK, HAS_NU, HAS_F, NUMASK>();
+  cudaError_t e = prep2t<MK, HAS_NU, FK, NUMASK>();
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -577,15 +596,15 @@ cudaError_t launch2t(const P2T& p, dim3 grid, dim3 block, size_t smem, cudaStrea
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   if (pdl_enabled()) { cfg.attrs = at; cfg.numAttrs = 1; }
-  return cudaLaunchKernelEx(&cfg, Kern2T<MK, HAS_NU, HAS_F, NUMASK>::get(), p);
+  return cudaLaunchKernelEx(&cfg, Kern2T<MK, HAS_NU, FK, NUMASK>::get(), p);
 }
 
 // resident CTAs per SM for a block of `threads` threads and `smem` bytes of dynamic shared memory
-template <int MK, bool HAS_NU, bool HAS_F, bool NUMASK>
+template <int MK, bool HAS_NU, int FK, bool NUMASK>
 int occ2t(int threads, size_t smem) {
-  if (prep2t<MK, HAS_NU, HAS_F, NUMASK>() != cudaSuccess) return 0;
+  if (prep2t<MK, HAS_NU, FK, NUMASK>() != cudaSuccess) return 0;
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern2T<MK, HAS_NU, HAS_F, NUMASK>::get(),
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern2T<MK, HAS_NU, FK, NUMASK>::get(),
                                                     threads, smem) != cudaSuccess)
     return 0;
   return n;

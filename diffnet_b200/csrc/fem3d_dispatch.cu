@@ -95,6 +95,9 @@ int run3d(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
                    wsb, loss_out, loss_f32, stream, sms, &handled, link);
     if (rc != DN_OK || handled) return rc;
     if (link) return fail(DN_EINVAL, "a linked z-slab launch needs the streaming path (nx %% 4 == 0, aligned x-contiguous fields)");
+    if (k.lv)
+      return fail(DN_ENOSTREAM, "DN_F_LOAD_VECTOR: the streaming 3-D kernel cannot take this launch (nx %% 4, aligned "
+                  "x-contiguous fields, whole-domain ownership); pass f_gp instead");
   }
   vec4 = vec4 && ((uintptr_t)grad % 16 == 0);
   Plan3D pl = plan3d(g, vec4, sms);

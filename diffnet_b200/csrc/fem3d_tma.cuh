@@ -51,6 +51,10 @@ struct K3 {
   // q_m = n_m t^(order(m) - 1) c0 u_m with n_m = the number of directions mode m is differentiated in
   // (1, 2, 3 for the first-, second-, third-order modes): 7 products instead of 20 products + 5 sums.
   float2 c0_2t, c0_3tt;
+  // assembled load vector (FK == 2): nkb = -(S c_f) weighs the nodal energy b u, nkb_pre = nkb / kscale the nodal
+  // gradient share (added before the keep factor applies kscale)
+  float nkb;
+  float2 nkb_pre;
 };
 
 // Linked z-slab launch (include/diffnet_fem.h: dn_slab_link): the halo exchange of u and the loss
@@ -145,10 +149,13 @@ __device__ __forceinline__ void dir_q(float2 d0, float2 d1, float2 d2, float2 d3
   q0 = fma2(d3, P3, q0);   q1 = fma2(d3, P2, q1);   q2 = fma2(d3, P1, q2);   q3 = fma2(d3, P0, q3);
 }
 
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI = true, bool ISO = false>
+// FK: 0 no source term, 1 nodal source, 2 `f` is an assembled load vector (see Fem2T): its term is added per
+// node when the node's plane is gathered (finalize), not per element.
+template <int NM, bool VF, bool HAS_NU, int FK, bool NUMASK, bool MI = true, bool ISO = false>
 struct Fem3T {
-  static constexpr int NF = 1 + (HAS_NU ? 1 : 0) + (HAS_F ? 1 : 0) + (NUMASK ? 1 : 0) + NM + (VF ? 1 : 0);
-  static constexpr int F_U = 0, F_NU = 1, F_F = F_NU + (HAS_NU ? 1 : 0), F_NM = F_F + (HAS_F ? 1 : 0),
+  static constexpr bool HAS_F = (FK == 1), LV = (FK == 2);
+  static constexpr int NF = 1 + (HAS_NU ? 1 : 0) + (FK ? 1 : 0) + (NUMASK ? 1 : 0) + NM + (VF ? 1 : 0);
+  static constexpr int F_U = 0, F_NU = 1, F_F = F_NU + (HAS_NU ? 1 : 0), F_NM = F_F + (FK ? 1 : 0),
                        F_M = F_NM + (NUMASK ? 1 : 0), F_VF = F_M + NM;
 
   // x-stage of one node row (3 nodes -> 2 elements): s = (v0+v1, v1+v2), d = (v1-v0, v2-v1)
@@ -165,7 +172,7 @@ struct Fem3T {
   // the domain) lives in this warp; the common warps skip that work with one branch.
   static __device__ __forceinline__ void load_faces(const P3T& p, uint32_t a0, uint32_t bx4, uint32_t fs4,
                                                     bool has_right, bool phantom, bool edge_warp, Face& Uu,
-                                                    Face& Un, Face& Uf, float2& keep) {
+                                                    Face& Un, Face& Uf, float2& keep, float2& lb, float& lE) {
     float2 su[2], du[2], sn[2], dn_[2], sf[2], df[2];
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
@@ -195,9 +202,15 @@ struct Fem3T {
           if constexpr (NUMASK) n = (v[F_NM][e] > 0.5f) ? 0.f : n;
           nb[e] = n;
         }
-        if constexpr (HAS_F) fb[e] = v[F_F][e];
+        if constexpr (HAS_F || LV) fb[e] = v[F_F][e];
       }
       if (row == 0) keep = f2(fx[0] ? 0.f : p.k3.kscale, fx[1] ? 0.f : p.k3.kscale);
+      if constexpr (LV) {
+        if (row == 0) {      // the two nodes of row a this thread gathers and stores
+          lb = mul2(p.k3.nkb_pre, f2(fb[0], fb[1]));
+          lE = p.k3.nkb * (fb[0] * ub[0] + fb[1] * ub[1]);
+        }
+      }
       xs(ub, su[row], du[row]);
       if constexpr (HAS_NU) xs(nb, sn[row], dn_[row]);
       if constexpr (HAS_F) xs(fb, sf[row], df[row]);
@@ -395,9 +408,9 @@ __device__ __forceinline__ void wait_halo_flag(const int* flag, const int* step,
 }
 
 // LK: linked z-slab launch (dn_slab_link) -- separate instantiations, so that the plain kernels carry none of it
-template <int NM, bool VF, bool HAS_NU, bool HAS_F, bool NUMASK, bool MI, bool ISO, bool LK>
+template <int NM, bool VF, bool HAS_NU, int FK, bool NUMASK, bool MI, bool ISO, bool LK>
 __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_constant__ P3T p) {
-  using F = Fem3T<NM, VF, HAS_NU, HAS_F, NUMASK, MI, ISO>;
+  using F = Fem3T<NM, VF, HAS_NU, FK, NUMASK, MI, ISO>;
   constexpr int NF = F::NF;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[DN_T3_MAXT / 32];
@@ -540,7 +553,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
 
   // node planes alternate between two register sets: the upper faces of one layer are the
   // lower faces of the next (no copies)
-  struct Plane { Face u, n, f; float2 keep; };
+  struct Plane { Face u, n, f; float2 keep, lb; float lE; };
   Plane PA, PB;
   Face up;                                       // z-carry of the gradient (face-mode space), upper plane
   up.m0 = up.m1 = up.m2 = up.m3 = f2(0.f);
@@ -569,7 +582,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     ++st; cur += stage4; cbar += 8u;
     if (st == S) { st = 0; cur = row0; cbar -= 8u * S; phase ^= 1u; }
     mbar_wait_u32(cbar, phase);
-    F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, U.u, U.n, U.f, U.keep);
+    F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, U.u, U.n, U.f, U.keep, U.lb, U.lE);
   };
   auto refill = [&]() {                          // after the layer barrier: the oldest stage is free again
     if (warp == 0 && issued < npl) issue_plane();
@@ -585,22 +598,24 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     return f2(loa.x, loa.y + hia.x);
   };
   // after the barrier: gather the neighbours' shares for node row a, mask, store
-  auto finalize = [&](float2 Na01, float2 keep, const uint32_t po, const bool sto) {
+  auto finalize = [&](float2 Na01, float2 keep, const uint32_t po, const bool sto, const float2 lb, const float lE) {
     const float2 nb = lds64(a_nr + po);                            // row r-1, same lane
     const float ha = lds32(a_t4 + kHA - 4u + po);                  // row a from lane lx-1   (thread tid-1)
     const float hb = lds32(a_r4 - 4u + po);                        // row b of row r-1 from lane lx-1 (thread tid-LXT-1)
     float2 G = f2(Na01.x + nb.x + (ha + hb), Na01.y + nb.y);
+    if constexpr (F::LV) G = add2(G, lb);                          // load vector: -(c_f / kscale) b of the two nodes
     G = mul2(G, keep);
     if (sto) {
       if (st_a) *reinterpret_cast<float2*>(gptr) = G;
       if (resid && own_a) e32 += G.x * G.x + G.y * G.y;
+      if constexpr (F::LV) e32 += (!resid && own_a) ? lE : 0.f;    // ... and their energy -c_f b u, once, by the owner
     }
     gptr += plane_elems;
   };
 
   // ---- first two planes of the march (npl >= 2): nothing before the first
   mbar_wait_u32(cbar, phase);
-  F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, PA.u, PA.n, PA.f, PA.keep);
+  F::load_faces(p, cur, bx4, fs4, has_right, phantom, edge_warp, PA.u, PA.n, PA.f, PA.keep, PA.lb, PA.lE);
   arrive();
   load_next(PB);
   wait_all();
@@ -624,12 +639,13 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     up = gUp;
     const float2 Na01 = publish(face_to_rows(dF), po);
     arrive();              // this warp has read the stage of the U plane and published its sums of the L plane
-    const float2 keepL = L.keep;
+    const float2 keepL = L.keep, lbL = L.lb;
+    const float lEL = L.lE;
     if (s + 2 <= zl) load_next(L);      // the plane after U replaces L in registers
     wait_all();            // every warp has arrived: partial sums visible, the oldest stage is free
     refill();
-    if constexpr (LK) finalize(Na01, keepL, po, pl >= z0 && pl < z1);
-    else finalize(Na01, keepL, po, s >= z0);
+    if constexpr (LK) finalize(Na01, keepL, po, pl >= z0 && pl < z1, lbL, lEL);
+    else finalize(Na01, keepL, po, s >= z0, lbL, lEL);
   };
   int s = zf;
   for (; s + 1 < zl; s += 2) {
@@ -648,7 +664,7 @@ __global__ void __maxnreg__(DN_T3_REGS_OF(HAS_NU)) k_fem3d_tma(const __grid_cons
     const float2 Na01 = publish(face_to_rows(up), po);
     arrive();
     wait_all();
-    finalize(Na01, odd ? PB.keep : PA.keep, po, true);
+    finalize(Na01, odd ? PB.keep : PA.keep, po, true, odd ? PB.lb : PA.lb, odd ? PB.lE : PA.lE);
   }
   acc += (double)e32;
 
@@ -668,29 +684,29 @@ typedef int (*occ3t_fn)(int, size_t);
 launch3t_fn get_launch3t(int MK, int NU, int F, int NUMASK, int LK);
 occ3t_fn get_occ3t(int MK, int NU, int F, int NUMASK, int LK);
 
-template <int MK, int NUK, bool HAS_F, bool NUMASK, bool LK>
+template <int MK, int NUK, int FK, bool NUMASK, bool LK>
 struct Kern3T {
   // MK 0..3 / 4 / 5..7 as in fem2d_tma.cuh (5..7: mask_input = 0)
   static constexpr int NM = (MK == 4) ? 1 : (MK >= 5 ? MK - 4 : MK);
-  static auto get() { return k_fem3d_tma<NM, (MK == 4), (NUK == 1 || NUK == 2), HAS_F, NUMASK, (MK < 5), (NUK >= 2), LK>; }
+  static auto get() { return k_fem3d_tma<NM, (MK == 4), (NUK == 1 || NUK == 2), FK, NUMASK, (MK < 5), (NUK >= 2), LK>; }
 };
 
-template <int MK, int NUK, bool HAS_F, bool NUMASK, bool LK>
+template <int MK, int NUK, int FK, bool NUMASK, bool LK>
 cudaError_t prep3t() {
   static bool done[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  e = cudaFuncSetAttribute(Kern3T<MK, NUK, HAS_F, NUMASK, LK>::get(),
+  e = cudaFuncSetAttribute(Kern3T<MK, NUK, FK, NUMASK, LK>::get(),
                            cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
   if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
   return e;
 }
 
-template <int MK, int NUK, bool HAS_F, bool NUMASK, bool LK>
+template <int MK, int NUK, int FK, bool NUMASK, bool LK>
 cudaError_t launch3t(const P3T& p, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
-  cudaError_t e = prep3t<MK, NUK, HAS_F, NUMASK, LK>();
+  cudaError_t e = prep3t<MK, NUK, FK, NUMASK, LK>();
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -699,14 +715,14 @@ cudaError_t launch3t(const P3T& p, dim3 grid, dim3 block, size_t smem, cudaStrea
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   if (pdl_enabled()) { cfg.attrs = at; cfg.numAttrs = 1; }
-  return cudaLaunchKernelEx(&cfg, Kern3T<MK, NUK, HAS_F, NUMASK, LK>::get(), p);
+  return cudaLaunchKernelEx(&cfg, Kern3T<MK, NUK, FK, NUMASK, LK>::get(), p);
 }
 
-template <int MK, int NUK, bool HAS_F, bool NUMASK, bool LK>
+template <int MK, int NUK, int FK, bool NUMASK, bool LK>
 int occ3t(int threads, size_t smem) {
-  if (prep3t<MK, NUK, HAS_F, NUMASK, LK>() != cudaSuccess) return 0;
+  if (prep3t<MK, NUK, FK, NUMASK, LK>() != cudaSuccess) return 0;
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern3T<MK, NUK, HAS_F, NUMASK, LK>::get(), threads,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kern3T<MK, NUK, FK, NUMASK, LK>::get(), threads,
                                                     smem) != cudaSuccess)
     return 0;
   return n;

@@ -4,12 +4,14 @@
 //   NUK   0: nu == 1, 1: nodal nu, 2: nodal nu on an isotropic grid (hx == hy == hz: k applied per node),
 //         3: nu == 1 on an isotropic grid (one product per mode)
 #pragma once
+//   F     0 no source, 1 (true) nodal source, 2 assembled load vector (plain launches, no nu mask)
 //   LK    linked z-slab launch (dn_slab_link): scalar-valued Dirichlet sets (MK 0..3), no nu mask
 #define DN3T_COMBOS_PLAIN(X, MK)                                                                        \
   X(MK, 0, false, false, false) X(MK, 0, true, false, false) X(MK, 1, false, false, false)              \
   X(MK, 1, true, false, false) X(MK, 1, false, true, false) X(MK, 1, true, true, false)                 \
   X(MK, 2, false, false, false) X(MK, 2, true, false, false) X(MK, 2, false, true, false) X(MK, 2, true, true, false) \
-  X(MK, 3, false, false, false) X(MK, 3, true, false, false)
+  X(MK, 3, false, false, false) X(MK, 3, true, false, false)                                            \
+  X(MK, 0, 2, false, false) X(MK, 1, 2, false, false) X(MK, 2, 2, false, false) X(MK, 3, 2, false, false)
 #define DN3T_COMBOS_LINKED(X, MK)                                                                       \
   X(MK, 0, false, false, true) X(MK, 0, true, false, true) X(MK, 1, false, false, true)                 \
   X(MK, 1, true, false, true) X(MK, 2, false, false, true) X(MK, 2, true, false, true)                  \

@@ -207,7 +207,9 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
   if (!vec4 || fgp.p || ((uintptr_t)grad % 16 != 0)) return DN_OK;
   const bool iso = nu.p && k.kx == k.ky && k.kx == k.kz && k.kx != 0.f && env_i3("DN_T3_ISO", 1);
   const bool iso1 = !nu.p && k.kx == k.ky && k.kx == k.kz && env_i3("DN_T3_ISO", 1);
-  const int NU = nu.p ? (iso ? 2 : 1) : (iso1 ? 3 : 0), F = f.p ? 1 : 0, NMK = numask.p ? 1 : 0;
+  const int NU = nu.p ? (iso ? 2 : 1) : (iso1 ? 3 : 0), F = f.p ? (k.lv ? 2 : 1) : 0, NMK = numask.p ? 1 : 0;
+  // the load-vector term is nodal: with z-slab ownership a node plane has no single owner
+  if (k.lv && (link || g->z_own_hi > g->z_own_lo)) return DN_OK;
   int MKx = MK;
   if (!mask_input) {                     // operator apply: only the plain-mask, no-source variants exist
     if (MK == 0) MKx = 0;
@@ -268,6 +270,8 @@ int run3t(const Field& u, const Field& nu, const Field& f, const Field& fgp, con
     const float kf = k.kf / k.kx;
     p.k3.nkf = pr(-kf); p.k3.nkft = pr(-kf * t); p.k3.nkftt = pr(-kf * t * t); p.k3.nkfttt = pr(-kf * t * t * t);
   }
+  p.k3.nkb = -k.kb;
+  p.k3.nkb_pre = pr(-k.kb / p.k3.kscale);
   p.grad = grad;
   p.red.counter = (unsigned int*)workspace;
   p.red.partials = (double*)((char*)workspace + 64);

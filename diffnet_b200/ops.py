@@ -174,11 +174,78 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _check_f_gp(geom: Geometry, f_gp) -> torch.Tensor:
+    _require_cuda(f_gp, "f_gp")
+    ngp = geom.ngp_1d ** geom.nsd
+    fg = f_gp if f_gp.dim() == geom.nsd + 2 else f_gp.unsqueeze(0)
+    if tuple(fg.shape[1:]) != (ngp,) + geom.elems or fg.dtype != torch.float32:
+        raise L.DiffNetFEMError(
+            f"f_gp must be float32 (B|1, {ngp}, {geom.elems}); got {tuple(f_gp.shape)} {f_gp.dtype}")
+    return fg
+
+
+def load_vector(geom: Geometry, f_gp: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Assembled load vector b (Bf, *nodes) of a forcing given at the Gauss points (Bf = f_gp's batch, 1 when it is
+    shared by the batch): b_a = sum over elements and Gauss points of w_g N_a(g) f_gp.  The forcing term of the
+    reference's f_gp form (e8_2d_poisson_mms.py:154-175) is linear in u, so sum_g w_g f_g u_g = sum_a b_a u_a:
+    pass ``b`` as ``f`` with ``load_vector=True`` and the fused kernels stream 4 bytes per node instead of
+    4 * ngp bytes per element."""
+    fg = _check_f_gp(geom, f_gp).contiguous()
+    Bf = fg.shape[0]
+    dev = fg.device
+    if out is None:
+        out = _new_out((Bf,) + geom.spatial, dev)
+    g = _geom_struct(geom, Bf)
+    ffg = L.dn_field(fg.data_ptr(), fg.stride(0) if Bf > 1 else 0, 0, 0)
+    with _on_device(dev):
+        rc = L.lib().dn_fem_load_vector_f32(C.byref(ffg), C.byref(g), C.c_void_p(out.data_ptr()),
+                                            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    L.check(rc, "dn_fem_load_vector_f32")
+    return out
+
+
+# f_gp -> load vector, remembered per tensor OBJECT and version counter (an in-place update of f_gp re-assembles; a
+# new tensor at a recycled address is a different object and misses).  Small: a training loop has one or two f_gp.
+_LV_CACHE = []          # [(weakref(f_gp), version, geom key, b)]
+_LV_CACHE_MAX = 8
+USE_LOAD_VECTOR = os.environ.get("DN_LOAD_VECTOR", "1") != "0"
+
+
+def _cached_load_vector(geom: Geometry, f_gp: torch.Tensor) -> torch.Tensor:
+    import weakref
+    key = (geom.nsd, geom.spatial, geom.ngp_1d)
+    for i, (ref, ver, k, b) in enumerate(_LV_CACHE):
+        if ref() is f_gp and k == key:
+            if ver == f_gp._version:
+                return b
+            _LV_CACHE.pop(i)
+            break
+    _LV_CACHE[:] = [e for e in _LV_CACHE if e[0]() is not None][-(_LV_CACHE_MAX - 1):]
+    b = load_vector(geom, f_gp)
+    _LV_CACHE.append((weakref.ref(f_gp), f_gp._version, key, b))
+    return b
+
+
 def energy_raw(geom: Geometry, u, nu=None, f=None, f_gp=None, dirichlet=(), nu_zero_mask=None,
                c_k=1.0, c_f=1.0, scale=1.0, reduction="mean", want_grad=True, want_grad_nu=False,
-               z_own=None, mean_count=0.0, want_double=False):
+               z_own=None, mean_count=0.0, want_double=False, load_vector=False):
     """One fused launch.  Returns (loss 0-dim fp32, grad_u (B,*spatial) or None,
-    grad_nu or None[, loss fp64 0-dim])."""
+    grad_nu or None[, loss fp64 0-dim]).
+
+    ``load_vector=True``: ``f`` is an assembled load vector (``load_vector()``), not a nodal source.  A call with
+    ``f_gp`` takes that route by itself (assembling b once per f_gp tensor and version) whenever the streaming
+    kernels can run the launch, and reads f_gp in the general kernels otherwise."""
+    if (f_gp is not None and f is None and USE_LOAD_VECTOR and not load_vector and z_own is None
+            and not want_grad_nu):
+        _check_f_gp(geom, f_gp)
+        try:
+            return energy_raw(geom, u, nu=nu, f=_cached_load_vector(geom, f_gp), dirichlet=dirichlet,
+                              nu_zero_mask=nu_zero_mask, c_k=c_k, c_f=c_f, scale=scale, reduction=reduction,
+                              want_grad=want_grad, want_grad_nu=False, mean_count=mean_count,
+                              want_double=want_double, load_vector=True)
+        except L.DiffNetFEMError as e:
+            if e.code != L.DN_ENOSTREAM:
+                raise                      # anything else is a real error; DN_ENOSTREAM: the general kernels read f_gp
     keep = []
     uc = _canon(u, geom, "u")
     nuc = _canon(nu, geom, "nu") if nu is not None else None
@@ -186,19 +253,16 @@ def energy_raw(geom: Geometry, u, nu=None, f=None, f_gp=None, dirichlet=(), nu_z
     nzm = _canon(nu_zero_mask, geom, "nu_zero_mask") if nu_zero_mask is not None else None
     fg = None
     if f_gp is not None:
-        _require_cuda(f_gp, "f_gp")
-        ngp = geom.ngp_1d ** geom.nsd
-        fg = f_gp if f_gp.dim() == geom.nsd + 2 else f_gp.unsqueeze(0)
-        if tuple(fg.shape[1:]) != (ngp,) + geom.elems or fg.dtype != torch.float32:
-            raise L.DiffNetFEMError(
-                f"f_gp must be float32 (B|1, {ngp}, {geom.elems}); got {tuple(f_gp.shape)} {f_gp.dtype}")
-        fg = fg.contiguous()
+        fg = _check_f_gp(geom, f_gp).contiguous()
+    if load_vector and (fc is None or fg is not None):
+        raise L.DiffNetFEMError("load_vector=True: pass the assembled vector as f (and no f_gp)")
     masks_t = [m for m, _ in dirichlet] + [v for _, v in dirichlet if torch.is_tensor(v)]
     B = _batch_of(uc, nuc, fc, nzm, fg, *[_canon(m, geom, "mask") for m in masks_t])
     marr, nm = _masks_struct(dirichlet, geom, B, keep)
     dev = uc.device
     g = _geom_struct(geom, B, z_own, mean_count)
-    cs = L.dn_consts(float(c_k), float(c_f), float(scale), 0 if reduction == "mean" else 1, 0)
+    cs = L.dn_consts(float(c_k), float(c_f), float(scale), 0 if reduction == "mean" else 1,
+                     L.DN_F_LOAD_VECTOR if load_vector else 0)
     if reduction not in ("mean", "sum"):
         raise L.DiffNetFEMError("reduction must be 'mean' or 'sum'")
     grad = _new_out((B,) + geom.spatial, dev) if want_grad else None
@@ -263,13 +327,11 @@ class PreparedEnergy:
                     "a prepared call binds storage -- pass float32 tensors whose x axis is contiguous")
         fg = None
         if f_gp is not None:
-            _require_cuda(f_gp, "f_gp")
-            ngp = geom.ngp_1d ** geom.nsd
-            fg = f_gp if f_gp.dim() == geom.nsd + 2 else f_gp.unsqueeze(0)
-            if tuple(fg.shape[1:]) != (ngp,) + geom.elems or fg.dtype != torch.float32:
-                raise L.DiffNetFEMError(f"f_gp must be float32 (B|1, {ngp}, {geom.elems})")
+            fg = _check_f_gp(geom, f_gp)
             if not fg.is_contiguous():
                 raise L.DiffNetFEMError("prepare_energy: f_gp must be contiguous (a prepared call binds storage)")
+            if f is not None:
+                raise L.DiffNetFEMError("give f or f_gp, not both")
         masks_t = [m for m, _ in dirichlet] + [v for _, v in dirichlet if torch.is_tensor(v)]
         B = _batch_of(uc, nuc, fc, nzm, fg, *[_canon(m, geom, "mask") for m in masks_t])
         self._marr, self._nm = _masks_struct(dirichlet, geom, B, keep)
@@ -284,6 +346,14 @@ class PreparedEnergy:
             self._ffg = L.dn_field(fg.data_ptr(), fg.stride(0) if (fg.shape[0] == B and B > 1) else 0, 0, 0)
         self._fnz = _field(nzm, B, geom.nsd)
         self._has = (nuc is not None, fc is not None, fg is not None, nzm is not None)
+        # f_gp: the assembled load vector is what the streaming kernels read (re-assembled when f_gp's version
+        # counter moves); the first call falls back to the general kernels for good if they refuse the launch
+        self._lv = None
+        if fg is not None and link is None and z_own is None and USE_LOAD_VECTOR:
+            bvec = load_vector(geom, fg)
+            self._lv = (fg, fg._version, bvec, _field(bvec, B, geom.nsd),
+                        L.dn_consts(float(c_k), float(c_f), float(scale), 0 if reduction == "mean" else 1,
+                                    L.DN_F_LOAD_VECTOR))
         self._keep = (keep, uc, nuc, fc, nzm, fg)            # the views the pointers refer to
         lib = L.lib()
         self._fn = lib.dn_fem_energy_2d_f32 if geom.nsd == 2 else lib.dn_fem_energy_3d_f32
@@ -306,6 +376,19 @@ class PreparedEnergy:
                     None, C.c_void_p(self.loss.data_ptr()), C.c_void_p(stream))
                 L.check(rc, "dn_fem_energy_3d_linked_f32")
                 return self.loss, self.grad
+            if self._lv is not None:
+                fg, ver, bvec, fb, cs = self._lv
+                if fg._version != ver:
+                    load_vector(self.geom, fg, out=bvec)
+                    self._lv = (fg, fg._version, bvec, fb, cs)
+                rc = self._fn(C.byref(self._fu), C.byref(self._fnu) if hn else None, C.byref(fb), None, self._marr,
+                              self._nm, C.byref(self._fnz) if hz else None, C.byref(self._g), C.byref(cs),
+                              C.c_void_p(self.grad.data_ptr()), None, C.c_void_p(ws.data_ptr()), ws.numel(), None,
+                              C.c_void_p(self.loss.data_ptr()), C.c_void_p(stream))
+                if rc != L.DN_ENOSTREAM:
+                    L.check(rc, f"dn_fem_energy_{self.geom.nsd}d_f32")
+                    return self.loss, self.grad
+                self._lv = None
             rc = self._fn(C.byref(self._fu), C.byref(self._fnu) if hn else None, C.byref(self._ff) if hf else None,
                           C.byref(self._ffg) if hg else None, self._marr, self._nm,
                           C.byref(self._fnz) if hz else None, C.byref(self._g), C.byref(self._cs),

@@ -56,7 +56,9 @@ typedef enum dn_status {
   DN_EINVAL = -1,      /* bad shape / stride / null pointer / unsupported option */
   DN_EARCH = -2,       /* device is not sm_100 (B200) */
   DN_ECUDA = -3,       /* CUDA launch/runtime error, see dn_last_error() */
-  DN_EWORKSPACE = -4   /* workspace missing or too small */
+  DN_EWORKSPACE = -4,  /* workspace missing or too small */
+  DN_ENOSTREAM = -5    /* an option only the streaming kernels implement (DN_F_LOAD_VECTOR) was asked for a launch they
+                          cannot take (odd nx, unaligned or non-contiguous views, z-slab ownership): use f_gp instead */
 } dn_status;
 
 /* One fp32 field on the mesh nodes.  ptr == NULL means "absent". */
@@ -96,8 +98,15 @@ typedef struct dn_consts {
   double c_f;            /* multiplies u * f */
   double scale;          /* overall factor s (e.g. 0.5*(h/2)^2 in 0_base.py:51-52) */
   int32_t reduction;     /* 0 = mean over batch x elements, 1 = sum */
-  int32_t _pad;
+  int32_t flags;         /* DN_F_* bits; 0 = the reference's forms */
 } dn_consts;
+
+/* dn_consts.flags: `f` is not a nodal source but an ASSEMBLED load vector b_a = sum_e sum_g w_g N_a(g) f_g
+ * (dn_fem_load_vector_f32; reference-element weights, |J| stays in `scale`): the source term becomes
+ * -scale c_f sum_a b_a u_a.  Same loss and gradient as passing f_gp
+ * (the reference's forcing-at-Gauss-points form, e8_2d_poisson_mms.py:154-175) up to fp32 summation order, at 4
+ * instead of 4 ngp^nsd bytes per node and step when f_gp does not change between steps. */
+#define DN_F_LOAD_VECTOR 1
 
 /* which table a gp-eval call uses (DiffNetFEM.py:143-156) */
 typedef enum dn_gp_which { DN_GP_N = 0, DN_GP_DX = 1, DN_GP_DY = 2, DN_GP_DZ = 3 } dn_gp_which;
@@ -245,6 +254,17 @@ int dn_fem_gp_eval_general_f32(const dn_field* in, int nsd, int batch, int nx, i
                                int ngp_1d, const float* factors, float* out, void* stream);
 int dn_fem_gp_eval_general_adj_f32(const float* grad_out, int nsd, int batch, int nx, int ny, int nz, int nbf_1d,
                                    int ngp_1d, const float* factors, float* grad_in, void* stream);
+
+/*
+ * Load-vector assembly for the forcing-at-Gauss-points form (e8_2d_poisson_mms.py:154-175: f_gp * u_gp summed with
+ * the quadrature weights).  The term is LINEAR in u, so it equals sum_a b_a u_a with
+ *     b_a = sum over the elements e around node a, over Gauss points g:  w_g N_a(g) f_gp[e, g]
+ * (reference-element weights).  This call assembles b once; every later loss call passes it as `f` with
+ * dn_consts.flags = DN_F_LOAD_VECTOR and the streaming kernels read 4 bytes per node instead of 4 ngp^nsd per element.
+ * fgp: dense (B|1, ngp_1d^nsd, elems), stride_b = 0 -> one b for the whole batch; out: dense nodes
+ * (stride_b == 0 ? 1 : g->batch, [nz,] ny, nx), overwritten.  Uses g->nsd, batch, nx, ny, nz, ngp_1d.
+ */
+int dn_fem_load_vector_f32(const dn_field* fgp, const dn_geom* g, float* out, void* stream);
 
 /*
  * Device-side producers of the path's INPUT tensors (what the reference's dataset classes build on the host with
