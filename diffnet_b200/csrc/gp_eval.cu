@@ -13,6 +13,8 @@
 //   * Outputs are write-once: streaming stores (st.global.cs), so they do not evict the inputs from L2.
 //   * Adjoint: the x-neighbour's share travels by one warp shuffle per node row; a warp covers 31 node columns
 //     plus one provider lane on its left, so there are no shared-memory seams and no atomics (deterministic).
+#include <cstdlib>
+
 #include "gp_eval.cuh"
 
 namespace dn {
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
                                                             float* __restrict__ gin) {
   constexpr int NZ = (NSD == 3) ? 2 : 1;
   constexpr int NGP = (NSD == 3) ? NG * NG * NG : NG * NG;
+  constexpr bool PF = (NSD == 2 && NG == 2);     // table 0 of the next element row is loaded one row ahead
   const int nelx = nx - 1, nely = ny - 1, nelz = (NSD == 3) ? nz - 1 : 1;
   const int nzz = (NSD == 3) ? nz : 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -116,6 +119,12 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
   const long long gb = (long long)b * NGP * nel + (ev ? e : 0);
   float* orow = gin + (((long long)b * nzz + z) * ny + y0) * nx + (sv ? x : 0);
 
+  float pf[PF ? NGP : 1];
+  if constexpr (PF) {
+    const int ej0 = max(y0 - 1, 0);
+#pragma unroll
+    for (int G = 0; G < NGP; ++G) pf[G] = (ev && ej0 < nely) ? __ldg(m.gout[0] + gb + (long long)ej0 * nelx + G * nel) : 0.f;
+  }
   float carry = 0.f;                      // contribution of element row ej - 1 to node row ej (jb = 1), own + left share
   for (int ej = y0 - 1; ej < y1; ++ej) {
     // Q[jb][ib]: this element column's contribution (both layers around plane z, all tables) to its node
@@ -140,7 +149,10 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
               float s0 = 0.f, s1 = 0.f;
 #pragma unroll
               for (int ig = 0; ig < NG; ++ig) {
-                const float gv = __ldg(ge + (long long)((kg * NG + jg) * NG + ig) * nel);
+                const int G = (kg * NG + jg) * NG + ig;
+                float gv;
+                if (PF && w == 0) gv = pf[PF ? G : 0];
+                else gv = __ldg(ge + (long long)G * nel);
                 s0 += tb.c[0][ig][0] * gv;
                 s1 += tb.c[0][ig][1] * gv;
               }
@@ -152,6 +164,12 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
         }
       }
     }
+    if constexpr (PF) {                  // the next row's loads fly during the shuffles and the store
+      const int en = ej + 1;
+      const bool nv = ev && en < nely && en < y1;
+#pragma unroll
+      for (int G = 0; G < NGP; ++G) pf[G] = nv ? __ldg(m.gout[0] + gb + (long long)en * nelx + G * nel) : 0.f;
+    }
     // node (ej, x): own element's (jb = 0, ib = 0) + left element's (jb = 0, ib = 1) + the carry of row ej - 1
     const float l0 = __shfl_up_sync(0xffffffffu, Q[0][1], 1);
     const float l1 = __shfl_up_sync(0xffffffffu, Q[1][1], 1);
@@ -160,6 +178,114 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
       orow += nx;
     }
     carry = Q[1][0] + l1;
+  }
+}
+
+// ---- 3-D adjoint, z-marching --------------------------------------------------------------------------------------
+// The y-march above visits every element layer twice in 3-D (once per node plane it touches: 16 loads and two
+// passes of the table products per node; ncu: 491 thread instructions per node, issue-bound at 0.24 of the HBM
+// peak).  Here a thread owns ONE element column (e, ej) and marches UP in z: each element's ngp^3 values are loaded
+// once, reduced by the separable x-, y-, z-stages to the 8 corner shares Q[kb][jb][ib] (48 FMAs per table for
+// ngp = 2), and the shares meet at the nodes through
+//   z: a register carry (the kb = 1 shares of layer ek wait one iteration for plane ek + 1),
+//   x, y: one shared-memory exchange per layer (three 8-byte words per thread: the shares for the right, lower and
+//         lower-right neighbour threads; double-buffered, ONE __syncthreads per layer).
+// A CTA is LXW lanes (x) by kAdjR rows (y).  Its thread (lx, r) stores node (x = e, y = ej); in the first tile of
+// each direction every thread stores (node 0 has no element on its left / above it), later tiles overlap their
+// predecessor by one provider lane / row.  z-chunks re-run the layer below their first plane for the carry.
+constexpr int kAdjR = 8;
+
+template <int NG>
+__global__ void __launch_bounds__(64 * kAdjR) k_gp_eval_adj3(GpMultiAdj m, int nx, int ny, int nz, int ZC, int ntx,
+                                                             int nty, float* __restrict__ gin) {
+  constexpr int NGP = NG * NG * NG;
+  extern __shared__ float2 xch[];                       // [2 buffers][3 kinds][kAdjR][LXW]
+  const int LXW = blockDim.x / kAdjR;
+  const int lx = threadIdx.x % LXW, r = threadIdx.x / LXW;
+  const int nelx = nx - 1, nely = ny - 1, nelz = nz - 1;
+  int w_ = blockIdx.x;
+  const int tx = w_ % ntx; w_ /= ntx;
+  const int ty = w_ % nty; w_ /= nty;
+  const int nzc = (nz + ZC - 1) / ZC;
+  const int zc = w_ % nzc;
+  const int b = w_ / nzc;
+  const int e = (tx == 0) ? lx : LXW + (tx - 1) * (LXW - 1) - 1 + lx;        // element column == node column stored
+  const int ej = (ty == 0) ? r : kAdjR + (ty - 1) * (kAdjR - 1) - 1 + r;     // element row == node row stored
+  const bool st = (tx == 0 || lx >= 1) && e < nx && (ty == 0 || r >= 1) && ej < ny;
+  const bool ev = e < nelx && ej < nely;
+  const bool hasL = lx > 0, hasU = r > 0;
+  const int z0 = zc * ZC, z1 = min(nz, z0 + ZC);
+  const long long nel = (long long)nelx * nely * nelz;
+  const int layer = nelx * nely, gstep = (int)nel;      // NGP * nel < 2^31 (checked by the launcher)
+  const int ek0 = max(z0 - 1, 0);
+  const long long off0 = (long long)b * NGP * nel + (long long)ek0 * layer + (ev ? ej * nelx + e : 0);
+  float* out = gin + (((long long)b * nz + z0) * ny + (st ? ej : 0)) * nx + (st ? e : 0);
+  const int slot = r * LXW + lx, kind = kAdjR * LXW;
+
+  float g[NG == 2 ? NGP : 1];                           // table 0 of the next layer (ngp = 2), loaded one layer ahead
+  if constexpr (NG == 2) {
+#pragma unroll
+    for (int G = 0; G < NGP; ++G) g[G] = (ev && ek0 < nelz) ? __ldg(m.gout[0] + off0 + G * gstep) : 0.f;
+  }
+  float carry = 0.f;
+  long long off = off0;
+  for (int ek = ek0; ek < z1; ++ek, off += layer) {
+    float Q[2][2][2] = {{{0.f, 0.f}, {0.f, 0.f}}, {{0.f, 0.f}, {0.f, 0.f}}};
+    const bool lv = ev && ek < nelz;                    // the top plane of the domain has no layer above it
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      if (w >= m.nw) break;
+      const GpTables& tb = m.tb[w];
+      float t[NG][2][2];                                // [kg][jb][ib]: x- and y-stages done
+#pragma unroll
+      for (int kg = 0; kg < NG; ++kg) {
+        t[kg][0][0] = t[kg][0][1] = t[kg][1][0] = t[kg][1][1] = 0.f;
+#pragma unroll
+        for (int jg = 0; jg < NG; ++jg) {
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int ig = 0; ig < NG; ++ig) {
+            const int G = (kg * NG + jg) * NG + ig;
+            float gv;
+            if (NG == 2 && w == 0) gv = g[NG == 2 ? G : 0];
+            else gv = lv ? __ldg(m.gout[w] + off + G * gstep) : 0.f;
+            s0 = fmaf(tb.c[0][ig][0], gv, s0);
+            s1 = fmaf(tb.c[0][ig][1], gv, s1);
+          }
+          t[kg][0][0] = fmaf(tb.c[1][jg][0], s0, t[kg][0][0]); t[kg][0][1] = fmaf(tb.c[1][jg][0], s1, t[kg][0][1]);
+          t[kg][1][0] = fmaf(tb.c[1][jg][1], s0, t[kg][1][0]); t[kg][1][1] = fmaf(tb.c[1][jg][1], s1, t[kg][1][1]);
+        }
+      }
+#pragma unroll
+      for (int kg = 0; kg < NG; ++kg)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int jb = 0; jb < 2; ++jb)
+#pragma unroll
+            for (int ib = 0; ib < 2; ++ib) Q[kb][jb][ib] = fmaf(tb.c[2][kg][kb], t[kg][jb][ib], Q[kb][jb][ib]);
+    }
+    if constexpr (NG == 2) {                            // next layer's loads fly during the exchange
+      const bool nv = ev && ek + 1 < nelz && ek + 1 < z1;
+#pragma unroll
+      for (int G = 0; G < NGP; ++G) g[G] = nv ? __ldg(m.gout[0] + off + layer + G * gstep) : 0.f;
+    }
+    float2* buf = xch + (ek & 1) * 3 * kind;
+    buf[slot] = make_float2(Q[0][0][1], Q[1][0][1]);                 // for the right neighbour (same row)
+    buf[kind + slot] = make_float2(Q[0][1][0], Q[1][1][0]);          // for the thread below (same column)
+    buf[2 * kind + slot] = make_float2(Q[0][1][1], Q[1][1][1]);      // for the thread below-right
+    __syncthreads();
+    const float2 zero = make_float2(0.f, 0.f);
+    const float2 fl = hasL ? buf[slot - 1] : zero;
+    const float2 fu = hasU ? buf[kind + slot - LXW] : zero;
+    const float2 ful = (hasL && hasU) ? buf[2 * kind + slot - LXW - 1] : zero;
+    const float n0 = Q[0][0][0] + fl.x + (fu.x + ful.x);             // plane ek: complete with the carry
+    const float n1 = Q[1][0][0] + fl.y + (fu.y + ful.y);             // plane ek + 1: waits for the next layer
+    if (ek >= z0) {
+      if (st) __stcs(out, carry + n0);
+      out += (long long)ny * nx;
+    }
+    carry = n1;
   }
 }
 
@@ -235,8 +361,47 @@ cudaError_t launch_gp_eval(Field in, int B, int nx, int ny, int nz, int nsd, con
   return nsd == 2 ? launch_fwd<2>(in, B, nx, ny, 1, m, s) : launch_fwd<3>(in, B, nx, ny, nz, m, s);
 }
 
+static int env_gp(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// z-marching 3-D adjoint; false: not applicable (the y-march takes the call)
+static bool launch_adj3(int B, int nx, int ny, int nz, const GpMultiAdj& m, float* gin, cudaStream_t s, cudaError_t* err) {
+  const int NG = m.tb[0].n;
+  const long long nel = (long long)(nx - 1) * (ny - 1) * (nz - 1);
+  if (env_gp("DN_GP_ADJ3", 1) == 0 || NG * NG * NG * nel >= (1LL << 31)) return false;
+  const int LXW = nx <= 32 ? 32 : 64;
+  const int ntx = nx <= LXW ? 1 : 1 + (nx - LXW + LXW - 2) / (LXW - 1);
+  const int nty = ny <= kAdjR ? 1 : 1 + (ny - kAdjR + kAdjR - 2) / (kAdjR - 1);
+  // z chunks: enough CTAs for ~3 resident waves, chunks of >= 8 planes (one extra layer per chunk for the carry)
+  const long long tiles = (long long)B * ntx * nty;
+  long long want = (3LL * 148 * (2048 / (LXW * kAdjR)) + tiles - 1) / tiles;
+  if (want < 1) want = 1;
+  int ZC = (int)((nz + want - 1) / want);
+  if (ZC < 8) ZC = 8;
+  if (ZC > nz) ZC = nz;
+  ZC = env_gp("DN_GP_ADJ3_ZC", ZC);
+  const long long grid = tiles * ((nz + ZC - 1) / ZC);
+  if (grid > 0x7fffffffLL) return false;
+  const size_t smem = (size_t)2 * 3 * kAdjR * LXW * sizeof(float2);
+  const dim3 g((unsigned)grid), blk(LXW * kAdjR);
+  switch (NG) {
+    case 2: k_gp_eval_adj3<2><<<g, blk, smem, s>>>(m, nx, ny, nz, ZC, ntx, nty, gin); break;
+    case 3: k_gp_eval_adj3<3><<<g, blk, smem, s>>>(m, nx, ny, nz, ZC, ntx, nty, gin); break;
+    case 4: k_gp_eval_adj3<4><<<g, blk, smem, s>>>(m, nx, ny, nz, ZC, ntx, nty, gin); break;
+    default: return false;
+  }
+  *err = cudaGetLastError();
+  return true;
+}
+
 template <int NSD>
 static cudaError_t launch_adj(int B, int nx, int ny, int nz, GpMultiAdj m, float* gin, cudaStream_t s) {
+  if (NSD == 3) {
+    cudaError_t err = cudaSuccess;
+    if (launch_adj3(B, nx, ny, nz, m, gin, s, &err)) return err;
+  }
   const int nzz = (NSD == 3) ? nz : 1;
   const int nelx = nx - 1, nely = ny - 1, nelz = (NSD == 3) ? nz - 1 : 1;
   const int NG = m.tb[0].n;

@@ -373,6 +373,32 @@ def test_gp_eval_marching_kernels_against_oracle(B, D, H, W, ngp):
     assert float((ud.grad.cpu().double() - uo.grad).abs().max() / uo.grad.abs().max()) <= 2e-6
 
 
+@pytest.mark.parametrize("B,D,H,W,ngp", [(1, 2, 2, 2, 2), (3, 8, 8, 32, 2), (2, 9, 8, 33, 2), (1, 20, 17, 130, 2),
+                                         (2, 17, 15, 64, 2), (1, 10, 10, 40, 3), (1, 9, 9, 34, 4)])
+def test_gp_eval_adjoint_z_march_against_oracle_and_y_march(B, D, H, W, ngp, monkeypatch):
+    """The z-marching 3-D adjoint (k_gp_eval_adj3: one load per element value, shared-memory x/y exchange, register
+    z carry) over tile-exact, one-past-a-tile and multi-tile / multi-chunk sizes: against the transpose of the
+    oracle's conv in fp64, and against the y-marching kernel (DN_GP_ADJ3=0) it replaces."""
+    from helpers import oracle_for
+    fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_lengths=(1.3, 0.9, 0.6), domain_size=W, ngp_1d=ngp)
+    o = oracle_for(fem)
+    g = torch.Generator().manual_seed(D * 100 + W)
+    u = torch.randn(B, 1, D, H, W, generator=g)
+    for name in ("gauss_pt_evaluation", "gauss_pt_evaluation_der_x", "gauss_pt_evaluation_der_z"):
+        uo = u.double().requires_grad_(True)
+        ref = getattr(o, name)(uo)
+        cot = torch.randn(ref.shape, generator=g)
+        (gref,) = torch.autograd.grad(ref, uo, cot.double())
+        got = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("DN_GP_ADJ3", flag)
+            ud = u.to(DEV).requires_grad_(True)
+            (gd,) = torch.autograd.grad(getattr(fem, name)(ud), ud, cot.to(DEV))
+            got.append(gd.cpu())
+            assert float((gd.cpu().double() - gref).abs().max() / gref.abs().max()) <= 2e-6, (name, flag)
+        assert rel_l2(got[0], got[1]) <= 1e-6
+
+
 @pytest.mark.parametrize("shape", [(6, 16, 32), (10, 40, 72), (34, 64, 64)])
 def test_linked_slab_launch_loopback_one_gpu(shape):
     """dn_fem_energy_3d_linked_f32 on ONE GPU: a middle rank linked to itself (tools/linked_loopback.py) --
