@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
                                                             float* __restrict__ gin) {
   constexpr int NZ = (NSD == 3) ? 2 : 1;
   constexpr int NGP = (NSD == 3) ? NG * NG * NG : NG * NG;
-  constexpr bool PF = (NSD == 2 && NG == 2);     // table 0 of the next element row is loaded one row ahead
   const int nelx = nx - 1, nely = ny - 1, nelz = (NSD == 3) ? nz - 1 : 1;
   const int nzz = (NSD == 3) ? nz : 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -119,14 +118,12 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
   const long long gb = (long long)b * NGP * nel + (ev ? e : 0);
   float* orow = gin + (((long long)b * nzz + z) * ny + y0) * nx + (sv ? x : 0);
 
-  float pf[PF ? NGP : 1];
-  if constexpr (PF) {
-    const int ej0 = max(y0 - 1, 0);
-#pragma unroll
-    for (int G = 0; G < NGP; ++G) pf[G] = (ev && ej0 < nely) ? __ldg(m.gout[0] + gb + (long long)ej0 * nelx + G * nel) : 0.f;
-  }
+  // byte offset of (b, G = 0, layer z, element row ej, column e) inside a cotangent tensor: advanced by one element
+  // row per iteration (recomputing it from (b, ej) cost 45 integer instructions per row -- more than the arithmetic)
+  const long long rowb = 4LL * nelx, layerb = rowb * nely, gstepb = 4 * nel;
+  long long offb = 4 * gb + ((long long)(NSD == 3 ? z : 0) * nely + (y0 - 1)) * rowb;
   float carry = 0.f;                      // contribution of element row ej - 1 to node row ej (jb = 1), own + left share
-  for (int ej = y0 - 1; ej < y1; ++ej) {
+  for (int ej = y0 - 1; ej < y1; ++ej, offb += rowb) {
     // Q[jb][ib]: this element column's contribution (both layers around plane z, all tables) to its node
     // row jb (0: row ej, 1: row ej + 1) and node column ib (0: x = e, 1: x = e + 1)
     float Q[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
@@ -135,12 +132,12 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
       for (int kb = 0; kb < NZ; ++kb) {
         const int ek = z - kb;
         if (NSD == 3 && (ek < 0 || ek >= nelz)) continue;
-        const long long eoff = gb + ((long long)(NSD == 3 ? ek : 0) * nely + ej) * nelx;
+        const long long ob = offb - kb * layerb;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           if (w >= m.nw) break;
           const GpTables& tb = m.tb[w];
-          const float* ge = m.gout[w] + eoff;
+          const char* ge = reinterpret_cast<const char*>(m.gout[w]) + ob;
 #pragma unroll
           for (int kg = 0; kg < (NSD == 3 ? NG : 1); ++kg) {
             const float cz = (NSD == 3) ? tb.c[2][kg][kb] : 1.f;
@@ -149,10 +146,7 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
               float s0 = 0.f, s1 = 0.f;
 #pragma unroll
               for (int ig = 0; ig < NG; ++ig) {
-                const int G = (kg * NG + jg) * NG + ig;
-                float gv;
-                if (PF && w == 0) gv = pf[PF ? G : 0];
-                else gv = __ldg(ge + (long long)G * nel);
+                const float gv = __ldg(reinterpret_cast<const float*>(ge + ((kg * NG + jg) * NG + ig) * gstepb));
                 s0 += tb.c[0][ig][0] * gv;
                 s1 += tb.c[0][ig][1] * gv;
               }
@@ -163,12 +157,6 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
           }
         }
       }
-    }
-    if constexpr (PF) {                  // the next row's loads fly during the shuffles and the store
-      const int en = ej + 1;
-      const bool nv = ev && en < nely && en < y1;
-#pragma unroll
-      for (int G = 0; G < NGP; ++G) pf[G] = nv ? __ldg(m.gout[0] + gb + (long long)en * nelx + G * nel) : 0.f;
     }
     // node (ej, x): own element's (jb = 0, ib = 0) + left element's (jb = 0, ib = 1) + the carry of row ej - 1
     const float l0 = __shfl_up_sync(0xffffffffu, Q[0][1], 1);
