@@ -312,10 +312,15 @@ def time_ops(name, dev, K, reps=3):
     else:
         ngp = 2 ** nsd
         nel = B * (size - 1) ** nsd
-
-        def step(i):
-            return ops._gp_raw(fem.geometry, sets[i % nsets]["u"], 0)
         nbytes = dof * 4 + nel * ngp * 4
+        if kind == "gp_eval_adj":          # the transpose: reads the cotangent at the Gauss points, writes the nodes
+            cots = [torch.randn((B, ngp) + fem.geometry.elems, device=dev) for _ in range(max(2, min(nsets, 4)))]
+
+            def step(i):
+                return ops._gp_adj_raw(fem.geometry, cots[i % len(cots)], 0)
+        else:
+            def step(i):
+                return ops._gp_raw(fem.geometry, sets[i % nsets]["u"], 0)
     for i in range(3):
         step(i)
     torch.cuda.synchronize()
@@ -347,11 +352,13 @@ def time_ops(name, dev, K, reps=3):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak},
             "launches_per_step": 2 if kind == "resmin" else 1,
             "desc": ("residual form: operator pass + backward operator pass, " if kind == "resmin"
-                     else "gauss_pt_evaluation (un-fused, N table), ") + WORKLOADS[base][4]}
+                     else "gauss_pt_evaluation (un-fused, N table), " if kind == "gp_eval"
+                     else "adjoint of gauss_pt_evaluation (its autograd backward, N table), ") + WORKLOADS[base][4]}
 
 
 OPS_POINTS = ["resmin:poisson2d_param_256_b64", "resmin:poisson3d_param_64_b16",
-              "gp_eval:poisson2d_param_256_b64", "gp_eval:poisson3d_param_64_b16"]
+              "gp_eval:poisson2d_param_256_b64", "gp_eval:poisson3d_param_64_b16",
+              "gp_eval_adj:poisson2d_param_256_b64", "gp_eval_adj:poisson3d_param_64_b16"]
 
 
 def point_of(name, res, peak, clock_mhz=None):

@@ -534,6 +534,21 @@ def _gp_raw(geom: Geometry, t: torch.Tensor, which: int) -> torch.Tensor:
     return out
 
 
+def _gp_adj_raw(geom: Geometry, gout: torch.Tensor, which: int) -> torch.Tensor:
+    """Transpose of `_gp_raw`: cotangent (B, ngp, elems) -> nodes (B, *spatial)."""
+    gout = gout.contiguous()
+    B = gout.shape[0]
+    g = _geom_struct(geom, B)
+    gin = _new_out((B,) + geom.spatial, gout.device)
+    stream = torch.cuda.current_stream(gout.device).cuda_stream
+    lib = L.lib()
+    fn = lib.dn_fem_gp_eval_adj_2d_f32 if geom.nsd == 2 else lib.dn_fem_gp_eval_adj_3d_f32
+    with _on_device(gout.device):
+        rc = fn(_ptr(gout), C.byref(g), which, _ptr(gin), C.c_void_p(stream))
+    L.check(rc, "dn_fem_gp_eval_adj")
+    return gin
+
+
 class GaussPointEvalFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, geom, which):
@@ -543,18 +558,7 @@ class GaussPointEvalFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
-        geom = ctx.geom
-        gout = gout.contiguous()
-        B = gout.shape[0]
-        g = _geom_struct(geom, B)
-        gin = _new_out((B,) + geom.spatial, gout.device)
-        stream = torch.cuda.current_stream(gout.device).cuda_stream
-        lib = L.lib()
-        fn = lib.dn_fem_gp_eval_adj_2d_f32 if geom.nsd == 2 else lib.dn_fem_gp_eval_adj_3d_f32
-        with _on_device(gout.device):
-            rc = fn(_ptr(gout), C.byref(g), ctx.which, _ptr(gin), C.c_void_p(stream))
-        L.check(rc, "dn_fem_gp_eval_adj")
-        return _like_input(gin, ctx.t_ref, geom), None, None
+        return _like_input(_gp_adj_raw(ctx.geom, gout, ctx.which), ctx.t_ref, ctx.geom), None, None
 
 
 def _gp_multi_raw(geom: Geometry, t: torch.Tensor, whichs: Sequence[int]):
