@@ -310,7 +310,9 @@ static int sm_count() {
 static int rows_per_chunk(long long columns_ctas, int rows) {
   // these kernels are latency-bound at low occupancy (ncu: 0.54 waves, long_scoreboard 9 per issue with
   // 8 CTAs per SM in the grid): fill the machine -- 16 resident 128-thread CTAs per SM, two waves of them
-  const long long want = 32LL * sm_count();                // CTAs in the grid
+  const char* ev = getenv("DN_GP_CTAS_PER_SM");
+  const int per_sm = (ev && atoi(ev) > 0) ? atoi(ev) : 32;
+  const long long want = (long long)per_sm * sm_count();   // CTAs in the grid
   long long chunks = (want + columns_ctas - 1) / columns_ctas;
   if (chunks < 1) chunks = 1;
   int ry = (int)((rows + chunks - 1) / chunks);

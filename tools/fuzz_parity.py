@@ -31,7 +31,8 @@ def case(i):
     B = rng.choice([1, 1, 2, 3, 5, 17])
     lengths = (1.0, rng.choice([1.0, 0.7]), rng.choice([1.0, 0.4]))
     cls = DiffNet2DFEM if nsd == 2 else DiffNet3DFEM
-    fem = cls(None, domain_sizes=sizes, domain_lengths=lengths, domain_size=nx)
+    ngp = rng.choice([2, 2, 2, 3])
+    fem = cls(None, domain_sizes=sizes, domain_lengths=lengths, domain_size=nx, ngp_1d=ngp)
     g = torch.Generator().manual_seed(rng.randint(0, 1 << 30))
     shape = (B, 1) + dims
     u = torch.randn(shape, generator=g)
@@ -46,6 +47,8 @@ def case(i):
     kw = {}
     if rng.random() < 0.8: kw["nu"] = nu
     if rng.random() < 0.7: kw["f"] = f
+    elif rng.random() < 0.7:      # forcing at the Gauss points: assembled load vector (streaming) vs f_gp read (general)
+        kw["f_gp"] = torch.randn((rng.choice([1, B]), ngp ** nsd) + tuple(d - 1 for d in dims), generator=g)
     if nm: kw["dirichlet"] = dirichlet
     if "nu" in kw and rng.random() < 0.2: kw["nu_zero_mask"] = m3
     if rng.random() < 0.3: kw["c_k"] = 0.5
@@ -64,13 +67,13 @@ def case(i):
     finally:
         os.environ.pop(key)
     torch.cuda.synchronize()
-    desc = f"case {i}: nsd={nsd} sizes={sizes} B={B} opts={sorted(kw)} nm={nm}"
+    desc = f"case {i}: nsd={nsd} sizes={sizes} B={B} ngp={ngp} opts={sorted(kw)} nm={nm}"
     assert torch.isfinite(gs).all() and torch.isfinite(ls), desc + " (non-finite / unwritten output)"
     el, eg = abs(float(ls) - float(lg)) / max(abs(float(lg)), 1e-30), rel(gs, gg)
     assert el < 5e-6 and eg < 5e-6, f"{desc}: streaming vs general loss {el:.2e} grad {eg:.2e}"
     ndof = B * dims[0] * dims[1] * (dims[2] if nsd == 3 else 1)
     if ndof <= 60000:
-        o = Q1Oracle(nsd=nsd, domain_sizes=sizes, domain_lengths=lengths, domain_size=nx, dtype=torch.float64)
+        o = Q1Oracle(nsd=nsd, domain_sizes=sizes, domain_lengths=lengths, domain_size=nx, ngp_1d=ngp, dtype=torch.float64)
         u64 = u.double().requires_grad_(True)
         kw64 = {k: (v.double() if torch.is_tensor(v) else ([(m.double(), val) for m, val in v] if k == "dirichlet" else v)) for k, v in kw.items()}
         lref = OL.energy_loss(o, u64, **kw64)

@@ -8,7 +8,7 @@ mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${tag}_smi.txt 2>&1
 python -m pytest tests -m gpu -x -q > $O/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $O/${tag}_pytest.log
 tail -3 $O/${tag}_pytest.log
-python tools/fuzz_parity.py ${FUZZ_SECONDS:-120} 7 > $O/${tag}_fuzz.log 2>&1; echo "fuzz rc=$?"; tail -3 $O/${tag}_fuzz.log
+python tools/fuzz_parity.py ${FUZZ_SECONDS:-90} 7 > $O/${tag}_fuzz.log 2>&1; echo "fuzz rc=$?"; tail -3 $O/${tag}_fuzz.log
 python bench.py > $O/${tag}_bench_n1.json 2> $O/${tag}_bench_n1.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 5 --warmup 1 > $O/${tag}_bench_ref.json 2>> $O/${tag}_bench_n1.err; echo "ref rc=$?"
 python tools/show_bench.py $O/${tag}_bench_n1.json 2>&1 | head -40
