@@ -50,7 +50,7 @@ def case(i):
     elif rng.random() < 0.7:      # forcing at the Gauss points: assembled load vector (streaming) vs f_gp read (general)
         kw["f_gp"] = torch.randn((rng.choice([1, B]), ngp ** nsd) + tuple(d - 1 for d in dims), generator=g)
     if nm: kw["dirichlet"] = dirichlet
-    if "nu" in kw and rng.random() < 0.2: kw["nu_zero_mask"] = m3
+    if "nu" in kw and "f_gp" not in kw and rng.random() < 0.2: kw["nu_zero_mask"] = m3     # f_gp + nu mask: not offered
     if rng.random() < 0.3: kw["c_k"] = 0.5
     if rng.random() < 0.2: kw["scale"] = 0.37
     if rng.random() < 0.2: kw["reduction"] = "sum"
