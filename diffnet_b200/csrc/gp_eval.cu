@@ -183,6 +183,13 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_eval_adj(GpMultiAdj m, int nx
 // predecessor by one provider lane / row.  z-chunks re-run the layer below their first plane for the carry.
 constexpr int kAdjR = 8;
 
+// keep a loop invariant in a register (ptxas otherwise re-derives strides from the kernel parameters with a chain of
+// integer multiplies in every iteration: 75 of the 220 instructions per layer of the first version)
+__device__ __forceinline__ long long pinned(long long v) {
+  asm volatile("" : "+l"(v));
+  return v;
+}
+
 template <int NG>
 __global__ void __launch_bounds__(64 * kAdjR) k_gp_eval_adj3(GpMultiAdj m, int nx, int ny, int nz, int ZC, int ntx,
                                                              int nty, float* __restrict__ gin) {
@@ -204,26 +211,34 @@ __global__ void __launch_bounds__(64 * kAdjR) k_gp_eval_adj3(GpMultiAdj m, int n
   const bool hasL = lx > 0, hasU = r > 0;
   const int z0 = zc * ZC, z1 = min(nz, z0 + ZC);
   const long long nel = (long long)nelx * nely * nelz;
-  const int layer = nelx * nely, gstep = (int)nel;      // NGP * nel < 2^31 (checked by the launcher)
   const int ek0 = max(z0 - 1, 0);
-  const long long off0 = (long long)b * NGP * nel + (long long)ek0 * layer + (ev ? ej * nelx + e : 0);
-  float* out = gin + (((long long)b * nz + z0) * ny + (st ? ej : 0)) * nx + (st ? e : 0);
-  const int slot = r * LXW + lx, kind = kAdjR * LXW;
+  // byte strides / offsets (NGP * nel < 2^31 elements: checked by the launcher)
+  const long long gsb = pinned(4 * nel);                                     // between Gauss points
+  const long long layerb = pinned(4LL * nelx * nely);                        // between element layers
+  const long long planeb = pinned(4LL * ny * nx);                            // between node planes
+  long long offb = 4 * ((long long)b * NGP * nel + (long long)ek0 * nelx * nely + (ev ? ej * nelx + e : 0));
+  const char* p0 = reinterpret_cast<const char*>(m.gout[0]) + offb;          // table 0, layer ek, this element column
+  char* out = reinterpret_cast<char*>(gin + (((long long)b * nz + z0) * ny + (st ? ej : 0)) * nx + (st ? e : 0));
+  const int kind = kAdjR * LXW;
+  float2* cur = xch + (r * LXW + lx) + (ek0 & 1) * 3 * kind;                 // this thread's slot in the layer's buffer
+  int flip = (ek0 & 1) ? -3 * kind : 3 * kind;                               // to the other buffer
 
   float g[NG == 2 ? NGP : 1];                           // table 0 of the next layer (ngp = 2), loaded one layer ahead
   if constexpr (NG == 2) {
+    const bool v0 = ev && ek0 < nelz;
+    const char* a = p0;
 #pragma unroll
-    for (int G = 0; G < NGP; ++G) g[G] = (ev && ek0 < nelz) ? __ldg(m.gout[0] + off0 + G * gstep) : 0.f;
+    for (int G = 0; G < NGP; ++G, a += gsb) g[G] = v0 ? __ldg(reinterpret_cast<const float*>(a)) : 0.f;
   }
   float carry = 0.f;
-  long long off = off0;
-  for (int ek = ek0; ek < z1; ++ek, off += layer) {
+  for (int ek = ek0; ek < z1; ++ek) {
     float Q[2][2][2] = {{{0.f, 0.f}, {0.f, 0.f}}, {{0.f, 0.f}, {0.f, 0.f}}};
     const bool lv = ev && ek < nelz;                    // the top plane of the domain has no layer above it
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       if (w >= m.nw) break;
       const GpTables& tb = m.tb[w];
+      const char* aw = reinterpret_cast<const char*>(m.gout[w]) + offb;
       float t[NG][2][2];                                // [kg][jb][ib]: x- and y-stages done
 #pragma unroll
       for (int kg = 0; kg < NG; ++kg) {
@@ -236,7 +251,7 @@ __global__ void __launch_bounds__(64 * kAdjR) k_gp_eval_adj3(GpMultiAdj m, int n
             const int G = (kg * NG + jg) * NG + ig;
             float gv;
             if (NG == 2 && w == 0) gv = g[NG == 2 ? G : 0];
-            else gv = lv ? __ldg(m.gout[w] + off + G * gstep) : 0.f;
+            else gv = lv ? __ldg(reinterpret_cast<const float*>(aw + G * gsb)) : 0.f;
             s0 = fmaf(tb.c[0][ig][0], gv, s0);
             s1 = fmaf(tb.c[0][ig][1], gv, s1);
           }
@@ -253,25 +268,29 @@ __global__ void __launch_bounds__(64 * kAdjR) k_gp_eval_adj3(GpMultiAdj m, int n
 #pragma unroll
             for (int ib = 0; ib < 2; ++ib) Q[kb][jb][ib] = fmaf(tb.c[2][kg][kb], t[kg][jb][ib], Q[kb][jb][ib]);
     }
+    p0 += layerb;
+    offb += layerb;
     if constexpr (NG == 2) {                            // next layer's loads fly during the exchange
       const bool nv = ev && ek + 1 < nelz && ek + 1 < z1;
+      const char* a = p0;
 #pragma unroll
-      for (int G = 0; G < NGP; ++G) g[G] = nv ? __ldg(m.gout[0] + off + layer + G * gstep) : 0.f;
+      for (int G = 0; G < NGP; ++G, a += gsb) g[G] = nv ? __ldg(reinterpret_cast<const float*>(a)) : 0.f;
     }
-    float2* buf = xch + (ek & 1) * 3 * kind;
-    buf[slot] = make_float2(Q[0][0][1], Q[1][0][1]);                 // for the right neighbour (same row)
-    buf[kind + slot] = make_float2(Q[0][1][0], Q[1][1][0]);          // for the thread below (same column)
-    buf[2 * kind + slot] = make_float2(Q[0][1][1], Q[1][1][1]);      // for the thread below-right
+    cur[0] = make_float2(Q[0][0][1], Q[1][0][1]);                    // for the right neighbour (same row)
+    cur[kind] = make_float2(Q[0][1][0], Q[1][1][0]);                 // for the thread below (same column)
+    cur[2 * kind] = make_float2(Q[0][1][1], Q[1][1][1]);             // for the thread below-right
     __syncthreads();
     const float2 zero = make_float2(0.f, 0.f);
-    const float2 fl = hasL ? buf[slot - 1] : zero;
-    const float2 fu = hasU ? buf[kind + slot - LXW] : zero;
-    const float2 ful = (hasL && hasU) ? buf[2 * kind + slot - LXW - 1] : zero;
+    const float2 fl = hasL ? cur[-1] : zero;
+    const float2 fu = hasU ? cur[kind - LXW] : zero;
+    const float2 ful = (hasL && hasU) ? cur[2 * kind - LXW - 1] : zero;
+    cur += flip;
+    flip = -flip;
     const float n0 = Q[0][0][0] + fl.x + (fu.x + ful.x);             // plane ek: complete with the carry
     const float n1 = Q[1][0][0] + fl.y + (fu.y + ful.y);             // plane ek + 1: waits for the next layer
     if (ek >= z0) {
-      if (st) __stcs(out, carry + n0);
-      out += (long long)ny * nx;
+      if (st) __stcs(reinterpret_cast<float*>(out), carry + n0);
+      out += planeb;
     }
     carry = n1;
   }
