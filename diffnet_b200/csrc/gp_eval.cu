@@ -383,17 +383,38 @@ static bool launch_adj3(int B, int nx, int ny, int nz, const GpMultiAdj& m, floa
   const int LXW = nx <= 32 ? 32 : 64;
   const int ntx = nx <= LXW ? 1 : 1 + (nx - LXW + LXW - 2) / (LXW - 1);
   const int nty = ny <= kAdjR ? 1 : 1 + (ny - kAdjR + kAdjR - 2) / (kAdjR - 1);
-  // z chunks: enough CTAs for ~3 resident waves, chunks of >= 8 planes (one extra layer per chunk for the carry)
+  // z chunks: a CTA costs (ZC + 1 layers + a prologue worth ~3 layers) and the grid runs in ceil(grid / slots) waves.
+  // Measured at 64^3 x 16 (144 tiles, 444 slots): ZC = 22 (432 CTAs, one full wave) 37.8 us, 11 (1.95 waves) 39.3,
+  // 32 (0.65) 41.9, 8 (2.59) 42.8, 16 (1.30) 43.8 -- the order of this cost.
   const long long tiles = (long long)B * ntx * nty;
-  long long want = (3LL * 148 * (2048 / (LXW * kAdjR)) + tiles - 1) / tiles;
-  if (want < 1) want = 1;
-  int ZC = (int)((nz + want - 1) / want);
-  if (ZC < 8) ZC = 8;
-  if (ZC > nz) ZC = nz;
+  const size_t smem = (size_t)2 * 3 * kAdjR * LXW * sizeof(float2);
+  static int occ_cache[64][3][2] = {};                 // [device][NG - 2][LXW == 64]
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = 0; }
+  if (NG < 2 || NG > 4) return false;
+  int& per_sm = occ_cache[dev][NG - 2][LXW == 64];
+  cudaError_t oe = cudaSuccess;
+  if (per_sm < 1) switch (NG) {
+    case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gp_eval_adj3<2>, LXW * kAdjR, smem); break;
+    case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gp_eval_adj3<3>, LXW * kAdjR, smem); break;
+    case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gp_eval_adj3<4>, LXW * kAdjR, smem); break;
+    default: return false;
+  }
+  if (oe != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+  const long long slots = (long long)per_sm * sm_count();
+  int ZC = nz;
+  long long best = -1;
+  for (int nzc = 1; nzc <= (nz + 3) / 4; ++nzc) {
+    const int zc = (nz + nzc - 1) / nzc;
+    const long long grid = tiles * ((nz + zc - 1) / zc);
+    const long long cost = ((grid + slots - 1) / slots) * (zc + 4);
+    if (best < 0 || cost < best) { best = cost; ZC = zc; }
+  }
   ZC = env_gp("DN_GP_ADJ3_ZC", ZC);
+  if (ZC < 1) ZC = 1;
+  if (ZC > nz) ZC = nz;
   const long long grid = tiles * ((nz + ZC - 1) / ZC);
   if (grid > 0x7fffffffLL) return false;
-  const size_t smem = (size_t)2 * 3 * kAdjR * LXW * sizeof(float2);
   const dim3 g((unsigned)grid), blk(LXW * kAdjR);
   switch (NG) {
     case 2: k_gp_eval_adj3<2><<<g, blk, smem, s>>>(m, nx, ny, nz, ZC, ntx, nty, gin); break;
