@@ -8,8 +8,8 @@
 //     two element rows is loaded once and kept in registers, element rows contribute to the node rows above and
 //     below through a register carry.  Lanes run along x: every load and store instruction of a warp covers 32
 //     consecutive floats.  No integer division in the loop (the grid is (x chunks, y chunks, plane * batch)).
-//   * All requested tables (N, d/dx, d/dy, d/dz) are evaluated in ONE pass over the input (GpMulti): a loss body
-//     that needs u, u_x, u_y at the Gauss points streams u once instead of three times.
+//   * Several tables (N, d/dx, d/dy, d/dz) are requested in ONE call (GpMulti).  The kernels can evaluate them in one
+//     pass over the input, but the op is write-bound and one table per pass measured faster (launch_gp_eval).
 //   * Outputs are write-once: streaming stores (st.global.cs), so they do not evict the inputs from L2.
 //   * Adjoint: the x-neighbour's share travels by one warp shuffle per node row; a warp covers 31 node columns
 //     plus one provider lane on its left, so there are no shared-memory seams and no atomics (deterministic).
@@ -367,7 +367,20 @@ static cudaError_t launch_fwd(Field in, int B, int nx, int ny, int nz, GpMulti m
 }
 
 cudaError_t launch_gp_eval(Field in, int B, int nx, int ny, int nz, int nsd, const GpMulti& m, cudaStream_t s) {
-  return nsd == 2 ? launch_fwd<2>(in, B, nx, ny, 1, m, s) : launch_fwd<3>(in, B, nx, ny, nz, m, s);
+  // Tables per pass over the input (DN_GP_TABLES_PER_PASS, default 1).  The forward is WRITE-bound (4 B read against
+  // 4 ngp B written per node and table), so sharing the read buys little, and a pass that writes 12-32 output streams
+  // per thread runs at a lower fraction of the peak: measured 256^2 x 64, 3 tables: 70.4 / 65.6 / 61.7 us with
+  // 4 / 2 / 1 tables per pass; 64^3 x 16, 4 tables: 204.7 / 164.8 / 136.1 us.
+  const char* ev = getenv("DN_GP_TABLES_PER_PASS");
+  int per = (ev && atoi(ev) > 0) ? atoi(ev) : 1;
+  for (int w0 = 0; w0 < m.nw; w0 += per) {
+    GpMulti part;
+    part.nw = (m.nw - w0 < per) ? m.nw - w0 : per;
+    for (int w = 0; w < part.nw; ++w) { part.tb[w] = m.tb[w0 + w]; part.out[w] = m.out[w0 + w]; }
+    cudaError_t e = nsd == 2 ? launch_fwd<2>(in, B, nx, ny, 1, part, s) : launch_fwd<3>(in, B, nx, ny, nz, part, s);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 static int env_gp(const char* name, int dflt) {

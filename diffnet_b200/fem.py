@@ -328,7 +328,7 @@ class DiffNetFEM(PDE):
         return ops.gp_eval_general(tensor, 1, self.nbf_1d, self.ngp_1d, fac)
 
     def gauss_pt_evaluation_all(self, tensor, which=None):
-        """(gauss_pt_evaluation(t), _der_x(t), _der_y(t)[, _der_z(t)]) from ONE pass over `t` (new; the
+        """(gauss_pt_evaluation(t), _der_x(t), _der_y(t)[, _der_z(t)]) from ONE call (new; the
         reference makes one conv sweep per table, DiffNetFEM.py:143-156)."""
         which = which or (("N", "dx", "dy") + (("dz",) if self.nsd == 3 else ()))
         if self.fem_basis_deg != 1:

@@ -562,7 +562,7 @@ class GaussPointEvalFunction(torch.autograd.Function):
 
 
 def _gp_multi_raw(geom: Geometry, t: torch.Tensor, whichs: Sequence[int]):
-    """Several tables in one pass over `t` (dn_fem_gp_eval_multi_*): a tuple of (B, ngp, elems) tensors."""
+    """Several tables in one call (dn_fem_gp_eval_multi_*): a tuple of (B, ngp, elems) tensors."""
     tc = _canon(t, geom, "tensor")
     B = tc.shape[0]
     g = _geom_struct(geom, B)
@@ -695,7 +695,7 @@ def gp_eval(geom: Geometry, t: torch.Tensor, which: str = "N") -> torch.Tensor:
 
 
 def gp_eval_multi(geom: Geometry, t: torch.Tensor, which: Sequence[str] = ("N", "dx", "dy")):
-    """(gauss_pt_evaluation(t), ..._der_x(t), ...) for the listed tables from ONE pass over `t`."""
+    """(gauss_pt_evaluation(t), ..._der_x(t), ...) for the listed tables from ONE call (and one backward pass over all cotangents)."""
     whichs = tuple(_WHICH[w] for w in which)
     if not 1 <= len(whichs) <= 4 or (geom.nsd == 2 and 3 in whichs):
         raise ValueError(f"which={which!r}: 1..4 tables out of N, dx, dy" + (", dz" if geom.nsd == 3 else ""))

@@ -226,7 +226,7 @@ int dn_fem_gp_eval_adj_2d_f32(const float* grad_out, const dn_geom* g, int which
 int dn_fem_gp_eval_adj_3d_f32(const float* grad_out, const dn_geom* g, int which, float* grad_in,
                               void* stream);
 /*
- * Several tables in ONE pass over the input: which[w] in {0: N, 1: d/dx, 2: d/dy, 3: d/dz}, nwhich <= 4,
+ * Several tables in ONE call (one table per pass by default: the op is write-bound, see gp_eval.cu): which[w] in {0: N, 1: d/dx, 2: d/dy, 3: d/dz}, nwhich <= 4,
  * outs[w] / grad_outs[w] dense as above.  A user loss() body that calls gauss_pt_evaluation(u),
  * gauss_pt_evaluation_der_x(u), gauss_pt_evaluation_der_y(u) (e.g. examples/poisson/single_instance/
  * 14_helmholtz_mms.py:50-59) streams u once; the adjoint sums the cotangents of all tables in one launch.

@@ -1,3 +1,2 @@
 #!/bin/bash
-python -m pytest tests/test_gpu_parity_3d.py tests/test_gpu_parity_2d.py -x -q -k "gp_eval or unfused" 2>&1 | tail -2
-python tools/gp_probe.py 20 2>&1 | grep "kernel"
+for t in 4 2 1; do echo "TABLES_PER_PASS=$t"; DN_GP_TABLES_PER_PASS=$t python tools/gp_probe.py 20 2>&1 | grep "tables"; done
