@@ -45,6 +45,13 @@ for fem, shape in ((DiffNet2DFEM(None, domain_size=256), (64, 1, 256, 256)), (Di
         torch.autograd.grad(held[i % 2], u_req[i % 2], cots[i % 2], retain_graph=True)
     timed(adj, 4 * nodes + 4 * shape[0] * ngp * nel, "adjoint (autograd.grad)")
 
+    heldm = [ops.gp_eval_multi(fem.geometry, u, ("N", "dx", "dy", "dz")[:len(which)]) for u in u_req[:2]]     # all tables: one adjoint call
+    cotm = [tuple(torch.randn_like(o) for o in heldm[0]) for _ in range(2)]
+
+    def adjm(i):
+        torch.autograd.grad(heldm[i % 2], u_req[i % 2], cotm[i % 2], retain_graph=True)
+    timed(adjm, 4 * nodes + 4 * len(which) * shape[0] * ngp * nel, f"adjoint, {len(which)} tables, one call")
+
 
 # device-side kernel durations (the eager numbers above include ~30 us of host / autograd time per call)
 from torch.profiler import ProfilerActivity, profile
