@@ -665,17 +665,25 @@ int dn_fem_load_vector_f32(const dn_field* fgp, const dn_geom* g, float* out, vo
     return fail(DN_EINVAL, "load_vector: nsd 2 or 3, batch >= 1, >= 2 nodes per direction");
   double gx[4], gw[4];
   if (gauss_rule(g->ngp_1d, gx, gw)) return fail(DN_EINVAL, "ngp_1d=%d (2..4)", g->ngp_1d);
-  LoadVec q;
-  memset(&q, 0, sizeof(q));
-  q.fgp = (const float*)fgp->ptr;
-  q.sb = fgp->stride_b;
-  q.B = (fgp->stride_b == 0) ? 1 : g->batch;
-  q.nx = g->nx; q.ny = g->ny; q.nz = g->nsd == 3 ? g->nz : 1; q.nsd = g->nsd; q.ng = g->ngp_1d;
-  for (int i = 0; i < g->ngp_1d; ++i) {
-    q.wn[0][i] = (float)(gw[i] * 0.5 * (1.0 - gx[i]));
-    q.wn[1][i] = (float)(gw[i] * 0.5 * (1.0 + gx[i]));
-  }
-  return check_cuda(launch_load_vector(q, out, (cudaStream_t)stream), "load_vector launch");
+  // b = N^T (w f_gp): the transpose of the Gauss-point interpolation with the quadrature weights folded into the
+  // 1-D factors -- the tuned adjoint kernels (gp_eval.cu) do the assembly
+  GpMultiAdj m;
+  memset(&m, 0, sizeof(m));
+  m.nw = 1;
+  m.tb[0].n = g->ngp_1d;
+  for (int d = 0; d < 3; ++d)
+    for (int i = 0; i < g->ngp_1d; ++i) {
+      m.tb[0].c[d][i][0] = (float)(gw[i] * 0.5 * (1.0 - gx[i]));
+      m.tb[0].c[d][i][1] = (float)(gw[i] * 0.5 * (1.0 + gx[i]));
+    }
+  m.gout[0] = (const float*)fgp->ptr;
+  const int B = (fgp->stride_b == 0) ? 1 : g->batch;
+  const long long per_b = (long long)(g->nx - 1) * (g->ny - 1) * (g->nsd == 3 ? g->nz - 1 : 1);
+  long long ngp = 1;
+  for (int d = 0; d < g->nsd; ++d) ngp *= g->ngp_1d;
+  if (B > 1 && fgp->stride_b != ngp * per_b) return fail(DN_EINVAL, "load_vector: fgp must be dense (stride_b = ngp * elems)");
+  return check_cuda(launch_gp_eval_adj(B, g->nx, g->ny, g->nsd == 3 ? g->nz : 1, g->nsd, m, out, (cudaStream_t)stream),
+                    "load_vector launch");
 }
 
 int dn_peer_alloc(size_t bytes, void** ptr) {

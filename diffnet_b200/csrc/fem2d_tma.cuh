@@ -186,7 +186,7 @@ struct Acc2T {
 };
 
 // FK: 0 no source term, 1 nodal source f (interpolated to the Gauss points), 2 `f` is an ASSEMBLED load vector
-// b_a = sum_g w_g |J| N_a(g) f_g (dn_fem_load_vector_f32): the term -c_f sum_a b_a u_a is added per node when its
+// b_a = sum_e sum_g w_g N_a(g) f_g (dn_fem_load_vector_f32): the term -c_f sum_a b_a u_a is added per node when its
 // row closes -- what the reference's f-at-Gauss-points form (e8_2d_poisson_mms.py:154-175) costs once b exists.
 template <int NM, bool VF, bool HAS_NU, int FK, bool NUMASK, bool MI = true>
 struct Fem2T {

@@ -728,56 +728,6 @@ __global__ void __launch_bounds__(128) k_grad_nu_3d(GradNu3 q, float* __restrict
   }
 }
 
-// One thread per node: gathers its share from the (up to 2^nsd) elements around it.  Run once per f_gp (the result
-// is what the streaming kernels read every step), so it is written for clarity: x-coalesced loads, the re-reads
-// of an element by its other nodes hit L1/L2.
-__global__ void __launch_bounds__(128) k_load_vector(const LoadVec q, float* __restrict__ out) {
-  const int n = q.ng, nelx = q.nx - 1, nely = q.ny - 1, nelz = q.nsd == 3 ? q.nz - 1 : 1;
-  const long long gs = (long long)nelx * nely * nelz;
-  const long long total = (long long)q.B * q.nz * q.ny * q.nx;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % q.nx);
-    long long r = i / q.nx;
-    const int y = (int)(r % q.ny); r /= q.ny;
-    const int z = (int)(r % q.nz);
-    const int b = (int)(r / q.nz);
-    const float* base = q.fgp + (long long)b * q.sb;
-    float acc = 0.f;
-    for (int dz = 0; dz < (q.nsd == 3 ? 2 : 1); ++dz) {
-      const int ez = z - 1 + dz;              // element below (dz = 0: the node is its upper node) / above
-      if (q.nsd == 3 && (ez < 0 || ez >= nelz)) continue;
-      for (int dy = 0; dy < 2; ++dy) {
-        const int ey = y - 1 + dy;
-        if (ey < 0 || ey >= nely) continue;
-        for (int dx = 0; dx < 2; ++dx) {
-          const int ex = x - 1 + dx;
-          if (ex < 0 || ex >= nelx) continue;
-          const float* e = base + ((long long)(q.nsd == 3 ? ez : 0) * nely + ey) * nelx + ex;
-          for (int kg = 0; kg < (q.nsd == 3 ? n : 1); ++kg) {
-            const float wz = q.nsd == 3 ? q.wn[1 - dz][kg] : 1.f;
-            for (int jg = 0; jg < n; ++jg) {
-              const float wy = wz * q.wn[1 - dy][jg];
-              float rsum = 0.f;
-              for (int ig = 0; ig < n; ++ig)
-                rsum = fmaf(q.wn[1 - dx][ig], __ldg(e + (long long)((kg * n + jg) * n + ig) * gs), rsum);
-              acc = fmaf(wy, rsum, acc);
-            }
-          }
-        }
-      }
-    }
-    out[i] = acc;
-  }
-}
-
-cudaError_t launch_load_vector(const LoadVec& q, float* out, cudaStream_t s) {
-  const long long total = (long long)q.B * q.nz * q.ny * q.nx;
-  long long g = (total + 127) / 128;
-  const long long cap = 64LL * sm_count();
-  k_load_vector<<<(int)(g > cap ? cap : (g < 1 ? 1 : g)), 128, 0, s>>>(q, out);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_grad_nu_3d(const GradNu3& q, float* out, cudaStream_t s) {
   const long long total = (long long)q.B * q.nz * q.ny * q.nx;
   long long g = (total + 127) / 128;

@@ -47,16 +47,6 @@ struct GradNu3 {
 
 cudaError_t launch_grad_nu_3d(const GradNu3& q, float* out, cudaStream_t s);
 
-// Load-vector assembly b_a = sum_e sum_g w_g N_a(g) f_g from f at the Gauss points (reference-element weights;
-// |J| stays in dn_consts.scale).  wn[side][q] = w_q (1 -+ x_q) / 2: 1-D weight x shape function of the element's
-// left (0) / right (1) node.  fgp dense (B|1, ngp, elems) with batch stride sb (0: broadcast -> out has batch 1).
-struct LoadVec {
-  const float* fgp;
-  long long sb;
-  int B, nx, ny, nz, nsd, ng;
-  float wn[2][4];
-};
-cudaError_t launch_load_vector(const LoadVec& q, float* out, cudaStream_t s);
 cudaError_t launch_scale(float* x, size_t n, const float* factor_dev, cudaStream_t s);
 
 }  // namespace dn
