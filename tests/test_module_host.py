@@ -58,3 +58,38 @@ def test_user_subclass_contract():
     p = Poisson(torch.nn.Identity(), domain_size=16, batch_size=4, learning_rate=1e-2)
     opts, scheds = p.configure_optimizers() if list(p.network.parameters()) else ([None], [])
     assert p.geometry.nx == 16 and p.geometry.hx == pytest.approx(1 / 15)
+
+
+def test_load_vector_cache_host_logic(monkeypatch):
+    """ops._cached_load_vector (the f_gp -> assembled load vector memo, host side only; the assembly kernel is
+    replaced by a counter): one assembly per tensor OBJECT and version, re-assembly after an in-place update, a new
+    tensor with equal contents is a different key, dead tensors leave the cache, the cache is bounded."""
+    from diffnet_b200 import ops
+    fem = DiffNet2DFEM(None, domain_size=16)
+    calls = []
+
+    def fake(geom, f_gp, out=None):
+        calls.append(f_gp._version)
+        return torch.zeros((f_gp.shape[0],) + geom.spatial)
+    monkeypatch.setattr(ops, "load_vector", fake)
+    monkeypatch.setattr(ops, "_LV_CACHE", [])
+    f = torch.randn(1, 4, 15, 15)
+    b0 = ops._cached_load_vector(fem.geometry, f)
+    assert ops._cached_load_vector(fem.geometry, f) is b0 and len(calls) == 1          # hit
+    f.mul_(2.0)                                                                         # version counter moves
+    b1 = ops._cached_load_vector(fem.geometry, f)
+    assert b1 is not b0 and len(calls) == 2 and len(ops._LV_CACHE) == 1
+    g = f.clone()                                                                       # equal contents, other object
+    ops._cached_load_vector(fem.geometry, g)
+    assert len(calls) == 3 and len(ops._LV_CACHE) == 2
+    fem3 = DiffNet2DFEM(None, domain_size=16, ngp_1d=3)                                 # same tensor, other rule: other key
+    ops._cached_load_vector(fem3.geometry, f)
+    assert len(calls) == 4
+    del g
+    import gc
+    gc.collect()
+    keep = [torch.randn(1, 4, 15, 15) for _ in range(2 * ops._LV_CACHE_MAX)]
+    for t in keep:
+        ops._cached_load_vector(fem.geometry, t)
+    assert len(ops._LV_CACHE) <= ops._LV_CACHE_MAX
+    assert all(ref() is not None for ref, *_ in ops._LV_CACHE)
