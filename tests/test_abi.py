@@ -60,6 +60,19 @@ def test_struct_layout_matches_c(tmp_path):
     assert got == want
 
 
+def test_status_codes_and_flags_match_the_header(tmp_path):
+    """dn_status values, DN_F_LOAD_VECTOR and offsetof(dn_consts, flags) as gcc sees them in the header against _lib.py."""
+    src = tmp_path / "codes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "diffnet_fem.h"\n'
+                   'int main(){printf("%d %d %d %d %d %d %d %zu\\n", DN_OK, DN_EINVAL, DN_EARCH, DN_ECUDA, DN_EWORKSPACE,'
+                   ' DN_ENOSTREAM, DN_F_LOAD_VECTOR, offsetof(dn_consts, flags)); return 0;}\n')
+    exe = tmp_path / "codes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    assert got == [L.DN_OK, L.DN_EINVAL, L.DN_EARCH, L.DN_ECUDA, L.DN_EWORKSPACE, L.DN_ENOSTREAM, L.DN_F_LOAD_VECTOR,
+                   L.dn_consts.flags.offset]
+
+
 def test_workspace_query_is_host_only(lib):
     g = L.dn_geom(2, 64, 256, 256, 1, 2, 1 / 255, 1 / 255, 0.0, 0, 0, 0.0)
     n = lib.dn_fem_workspace_bytes(C.byref(g))
