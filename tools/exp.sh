@@ -1,3 +1,5 @@
 #!/bin/bash
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python -m pytest tests/test_gpu_parity_3d.py tests/test_gpu_parity_2d.py -m gpu -x -q -k "randomised or gauss_points or more_gauss" 2>&1 | tail -2
+# tools/exp.sh -- scratch driver for ONE short GPU-box call (`gpurun -- 'bash tools/exp.sh'`): edit, run, read
+# gpurun_out/.  The last use: the full gpu suite at the head of the tree.
+O=gpurun_out; mkdir -p $O
+python -m pytest tests -m gpu -x -q > $O/exp_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/exp_pytest.log
