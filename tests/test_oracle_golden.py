@@ -120,3 +120,43 @@ def test_host_kl_recipe_against_the_reference_fields():
     nu = kl_diffusivity_2d(torch.from_numpy(g["kl.coeffs"]), 16)
     ref = torch.from_numpy(g["kl2d.inputs"][:, 0:1])
     assert float(((nu - ref).abs() / ref).max()) < 1e-6
+
+
+@pytest.mark.parametrize("nsd,sizes,ngp", [(2, (9, 7, 1), 2), (2, (6, 8, 1), 3), (3, (5, 4, 6), 2), (3, (4, 5, 4), 4)])
+def test_load_vector_identity_on_the_oracle(nsd, sizes, ngp):
+    """What the load-vector route (include/diffnet_fem.h: DN_F_LOAD_VECTOR) relies on, checked on the CPU oracle alone:
+    the reference's forcing term sum_g w_g f_g u_g (e8_2d_poisson_mms.py:154-175, u_gp from gauss_pt_evaluation) equals
+    sum_a b_a u_a with b_a = sum over the elements around node a and their Gauss points of w_g N_a(g) f_g -- the
+    closed form the CUDA assembly implements (1-D factors w_q (1 -+ x_q) / 2 per direction)."""
+    import numpy as np
+    from oracle.fem import Q1Oracle, gauss_rule
+    o = Q1Oracle(nsd=nsd, domain_sizes=sizes, domain_lengths=(1.0, 0.8, 0.6), domain_size=sizes[0], ngp_1d=ngp,
+                 dtype=torch.float64)
+    nx, ny, nz = sizes
+    sp = (ny, nx) if nsd == 2 else (nz, ny, nx)
+    el = tuple(d - 1 for d in sp)
+    g = torch.Generator().manual_seed(nsd * 10 + ngp)
+    u = torch.randn((2, 1) + sp, generator=g, dtype=torch.float64, requires_grad=True)
+    f_gp = torch.randn((2, ngp ** nsd) + el, generator=g, dtype=torch.float64)
+    w = o.gpw.double().reshape((1, -1) + (1,) * nsd)
+    term = (w * f_gp * o.gauss_pt_evaluation(u)).sum()
+    (b_ref,) = torch.autograd.grad(term, u)
+    gx, gw = gauss_rule(ngp)
+    gx, gw = np.asarray(gx, dtype=np.float64), np.asarray(gw, dtype=np.float64)
+    wn = np.stack([gw * 0.5 * (1 - gx), gw * 0.5 * (1 + gx)])            # [side][q]
+    F = f_gp.numpy().reshape((2,) + (ngp,) * nsd + el)                    # [b][kg][jg][ig][(ez,) ey, ex]
+    b = np.zeros((2,) + sp)
+    sides = [(0, slice(0, -1)), (1, slice(1, None))]                       # local node 0 -> element index = node index
+    if nsd == 2:
+        for jb, ys in sides:
+            for ib, xs in sides:
+                b[:, ys, xs] += np.einsum("j,i,bjiyx->byx", wn[jb], wn[ib], F)
+    else:
+        for kb, zs in sides:
+            for jb, ys in sides:
+                for ib, xs in sides:
+                    b[:, zs, ys, xs] += np.einsum("k,j,i,bkjizyx->bzyx", wn[kb], wn[jb], wn[ib], F)
+    err = np.abs(b - b_ref[:, 0].numpy()).max() / np.abs(b).max()
+    assert err < 1e-6, err          # the oracle's stencils are the reference's fp32 tables: equal to fp32 rounding
+    t = float(term.detach())
+    assert abs(t - float((torch.from_numpy(b) * u.detach()[:, 0]).sum())) <= 1e-6 * abs(t) + 1e-9
