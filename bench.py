@@ -538,6 +538,7 @@ def numa_local(dev_index):
         use = cpus & allowed
         if use and use != allowed:
             os.sched_setaffinity(0, use)
+            info["_prev_affinity"] = allowed
         info["cpus"] = len(use) if use else 0
         try:
             import ctypes
@@ -551,6 +552,19 @@ def numa_local(dev_index):
     except Exception as e:   # noqa: BLE001
         info["error"] = f"{type(e).__name__}: {e}"
     return info
+
+
+def numa_restore(info):
+    """Undo numa_local once the pinned buffers exist (the CPU legs that follow want every core)."""
+    try:
+        prev = info.pop("_prev_affinity", None)
+        if prev:
+            os.sched_setaffinity(0, prev)
+        if info.get("mempolicy") == "preferred":
+            import ctypes
+            ctypes.CDLL(None, use_errno=True).syscall(238, 0, None, ctypes.c_ulong(0))      # MPOL_DEFAULT
+    except Exception:   # noqa: BLE001
+        pass
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -739,6 +753,7 @@ def run_ours(args):
             copyref = copy_reference(dev, step_bytes)
         except Exception as e:   # noqa: BLE001
             copyref = {"error": f"{type(e).__name__}: {e}"}
+    numa_restore(numa)
     # ---- the other BASELINE configs and the north_star's named roofline points, measured the same way
     points = None
     if world == 1 and args.points and name == DEFAULT:
