@@ -112,6 +112,18 @@ def test_golden_vectors(golden):
         assert rel_l2(out.cpu(), g["gp." + key]) <= 1e-6, key
 
 
+def test_golden_forcing_at_gauss_points(golden):
+    """The real reference's 3-D module on the e8_3d_poisson_mms.py form (tests/golden/make_golden_fgp3d.py): Dirichlet
+    value field + f at the Gauss points, here through the assembled load vector of the streaming kernel (nx = 8)."""
+    g = golden("ref_3d_fgp")
+    X, Y, Z = (int(v) for v in g["sizes"])
+    fem = DiffNet3DFEM(None, domain_sizes=(X, Y, Z), domain_lengths=(1.0, 0.8, 0.5), domain_size=X)
+    loss, grad = run_energy(fem, g.t("u"), nu=g.t("nu"), f_gp=g.t("f_gp"), dirichlet=[(g.t("bc"), g.t("u_bc"))], c_k=0.5)
+    assert rel_scalar(loss, g["E3fgp.loss64"]) <= LOSS_RTOL and rel_l2(grad, g["E3fgp.grad64"]) <= GRAD_RTOL
+    hit = (g.t("bc") > 0.5).expand_as(grad)
+    assert torch.count_nonzero(grad[hit]) == 0
+
+
 def test_residual_form():
     B, D, H, W = 1, 9, 10, 12
     fem = DiffNet3DFEM(None, domain_sizes=(W, H, D), domain_size=W)

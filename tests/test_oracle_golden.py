@@ -160,3 +160,13 @@ def test_load_vector_identity_on_the_oracle(nsd, sizes, ngp):
     assert err < 1e-6, err          # the oracle's stencils are the reference's fp32 tables: equal to fp32 rounding
     t = float(term.detach())
     assert abs(t - float((torch.from_numpy(b) * u.detach()[:, 0]).sum())) <= 1e-6 * abs(t) + 1e-9
+
+
+def test_3d_forcing_at_gauss_points(golden):
+    """examples/poisson/mms/e8_3d_poisson_mms.py form (Dirichlet value field + f at the Gauss points) on the real
+    reference's 3-D module (tests/golden/make_golden_fgp3d.py): the oracle's energy_loss with f_gp reproduces it."""
+    g = golden("ref_3d_fgp")
+    X, Y, Z = (int(v) for v in g["sizes"])
+    fem = Q1Oracle(nsd=3, domain_sizes=(X, Y, Z), domain_lengths=tuple(float(v) for v in g["lengths"]), domain_size=X)
+    _check(g, "E3fgp", *_lg(lambda v: L.energy_loss(fem, v, nu=g.t("nu"), f_gp=g.t("f_gp"),
+                                                     dirichlet=[(g.t("bc"), g.t("u_bc"))], c_k=0.5), g.t("u")))
